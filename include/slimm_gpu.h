@@ -1,0 +1,205 @@
+/*
+ * slimm_gpu.h - C ABI of the B200-native SLIMM profiling hot path.
+ *
+ * The reference (seqan/slimm 0.3.4) has no plugin / FFI seam: the hot path is five member
+ * functions of `class slimm` mutating its members (reference src/slimm.hpp:92-165), called from
+ * `slimm::get_profiles()` at src/slimm.hpp:449 (analyze_alignments), :464 (filter_alignments),
+ * :485 (get_reads_lca_count) and :489 (write_abundance).  This header DEFINES the seam at those
+ * four call sites.  Every entry point names the reference code it replaces.  INTEGRATION.md shows
+ * the patch a maintainer of the reference would apply to call it.
+ *
+ * Conventions: plain C types only; host buffers are caller-owned, device memory is library-owned
+ * (unless handed in through slimm_gpu_push_device); every call returns 0 on success or a
+ * SLIMM_GPU_E* code (slimm_gpu_strerror / slimm_gpu_last_error give text); no exceptions cross the
+ * boundary; one controlling host thread per context.  There is no CPU fallback: without a CUDA
+ * device slimm_gpu_create fails with SLIMM_GPU_ENODEVICE.
+ *
+ * u32 arithmetic wraps exactly as in the reference; f32 results are IEEE binary32 computed with
+ * the reference's operation order ("exactness").
+ */
+#ifndef SLIMM_GPU_H
+#define SLIMM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIMM_LINEAGE_LENGTH 8 /* reference src/misc.hpp:24-35 taxa_ranks strain..superkingdom */
+
+enum {
+    SLIMM_GPU_OK = 0,
+    SLIMM_GPU_EINVAL = 1,     /* bad argument / record referencing a contig >= n_refs          */
+    SLIMM_GPU_ENODEVICE = 2,  /* no usable CUDA device (there is no CPU fallback)               */
+    SLIMM_GPU_ECUDA = 3,      /* a CUDA runtime call failed, see slimm_gpu_last_error           */
+    SLIMM_GPU_ENOMEM = 4,     /* device or pinned-host allocation failed                        */
+    SLIMM_GPU_ESTATE = 5,     /* stages called out of order                                     */
+    SLIMM_GPU_ERANGE = 6      /* more than 2^32-1 records (hits_count is u32 in the reference)  */
+};
+
+/* flags for slimm_gpu_config.flags */
+#define SLIMM_GPU_KEEP_UNIQ_COV2 1u /* also build uniq_cov2 bins (needed by -co / -ro outputs)        */
+#define SLIMM_GPU_READ_RESULTS 2u   /* keep per-read reassignment / LCA results for slimm_gpu_read_results */
+
+typedef struct slimm_gpu_ctx slimm_gpu_ctx;
+
+/* Per-sample constants.  Replaces the reference-contig initialisation loop of get_profiles(),
+ * reference src/slimm.hpp:420-445, and the reference_contig / bins_coverage constructors,
+ * src/reference_contig.hpp:77-82,129-145 (three zeroed histograms of len/w+1 bins per contig). */
+typedef struct {
+    uint32_t n_refs;            /* contigs in @SQ order                                             */
+    const uint32_t *ref_len;    /* [n_refs]   @SQ LN                                                */
+    const uint32_t *lineage;    /* [n_refs*8] db.ac__taxid[accession(g)]; zeros for unknown         */
+    uint32_t bin_width;         /* -w, or the average read length when 0 (src/slimm.hpp:412-413)    */
+    uint32_t avg_read_length;   /* get_avg_read_length(), src/misc.hpp:509-522                      */
+    uint64_t reserve_records;   /* initial capacity of the device record store (0: grow on demand)  */
+    int32_t device;             /* CUDA device ordinal                                              */
+    uint32_t flags;             /* SLIMM_GPU_*                                                      */
+} slimm_gpu_config;
+
+/* Scalars of the path; names follow the reference's members (src/slimm.hpp:105-118). */
+typedef struct {
+    uint32_t hits_count;          /* kept records                                   :212 */
+    uint32_t matches_count;       /* distinct reads                                 :257 */
+    uint32_t uniq_matches_count;  /* reads with one target (== uniq_hits_count)     :225,236 */
+    uint32_t uniq_matches_count2; /* reads with one surviving target                :387 */
+    uint32_t reference_count;     /* references with reads                          :264 */
+    uint32_t n_valid;             /* |valid_ref_ids|                                :361 */
+    uint32_t failed_by_cov;       /* -v counters                                    :365-376 */
+    uint32_t failed_by_uniq_cov;
+    uint32_t failed_by_min_read;
+    uint32_t min_reads;           /* -mr or 1+(R-1)/10000                           :458-459 */
+    float coverage_cut_off;       /* coverage_cut_off()                             :328-344 */
+    float uniq_coverage_cut_off;  /* uniq_coverage_cut_off()                        :672-688 */
+    uint64_t n_pairs;             /* distinct (read, ref) pairs = sum of reads_count */
+    uint64_t n_bins;              /* sum over contigs of len/w+1                     */
+    uint32_t input_was_sorted;    /* 1: read ids were non-decreasing, no device sort needed */
+    uint32_t reserved;
+} slimm_gpu_summary;
+
+const char *slimm_gpu_strerror(int code);
+const char *slimm_gpu_last_error(const slimm_gpu_ctx *ctx);
+int slimm_gpu_device_count(int *n);
+
+int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out);
+int slimm_gpu_destroy(slimm_gpu_ctx *ctx);
+/* New sample against the same contigs/database (directory mode; reference slimm::reset(),
+ * src/slimm.hpp:167-188).  bin_width / avg_read_length may change, 0 keeps the old value. */
+int slimm_gpu_reset(slimm_gpu_ctx *ctx, uint32_t bin_width, uint32_t avg_read_length);
+/* Run all kernels on this cudaStream_t (e.g. the caller's framework stream).  NULL: own stream. */
+int slimm_gpu_set_stream(slimm_gpu_ctx *ctx, void *cuda_stream);
+
+/* Pinned host buffers for the decode threads to pack batches into (cudaHostAlloc). */
+int slimm_gpu_host_alloc(void **p, uint64_t bytes);
+int slimm_gpu_host_free(void *p);
+
+/* Ingest: append a struct-of-arrays batch of KEPT records (flag&4 / rID==-1 records are dropped by
+ * the decoder, reference src/slimm.hpp:197) in file order.  read_id is the dense id of
+ * qName + ".1"/".2" (src/slimm.hpp:204-208).  Replaces the record loop of analyze_alignments,
+ * src/slimm.hpp:194-213.  Host variant: asynchronous H2D on a copy stream when the buffers are
+ * pinned; the buffers may be reused after slimm_gpu_sync_uploads.  Device variant: the caller's
+ * device arrays are used in place (zero copy; single batch; must outlive the run). */
+int slimm_gpu_push(slimm_gpu_ctx *ctx, const uint32_t *read_id, const uint32_t *ref_id,
+                   const int32_t *begin_pos, uint64_t n);
+int slimm_gpu_push_device(slimm_gpu_ctx *ctx, const uint32_t *d_read_id, const uint32_t *d_ref_id,
+                          const int32_t *d_begin_pos, uint64_t n);
+int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx);
+
+/* Stage 1 - coverage.  Replaces the per-read loop of analyze_alignments (src/slimm.hpp:219-257,
+ * read_stat::add_target src/read_stat.hpp:116-135, is_uniq :72-75): first-occurrence dedupe of
+ * (read, ref), scatter-add into the cov / uniq_cov bins.  Leaves THIS rank's partial histogram on
+ * the device; with several GPUs sum slimm_gpu_bins_device() across ranks before stage 2. */
+int slimm_gpu_coverage(slimm_gpu_ctx *ctx);
+/* Device pointer to the interleaved {cov, uniq_cov} u32 histogram (2*n_words_per... see DESIGN.md)
+ * for an in-place NCCL sum; n_u32 is the number of u32 words. */
+int slimm_gpu_bins_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
+/* Device pointer to the read-level partial counters {matches_count, uniq_matches_count} (2 x u64,
+ * summed across ranks together with the bins). */
+int slimm_gpu_counters_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u64);
+/* Tell the context the global number of kept records when records are sharded over ranks. */
+int slimm_gpu_set_global_hits(slimm_gpu_ctx *ctx, uint64_t hits);
+
+/* Stage 2 - reference filter.  Replaces none_zero_bin_count / cov_percent / uniq_cov_percent
+ * (src/reference_contig.hpp:84-91,148-155), coverage_cut_off / uniq_coverage_cut_off
+ * (src/slimm.hpp:328-344,672-688) with get_quantile_cut_off (src/misc.hpp:197-216) and the
+ * reference loop of filter_alignments (src/slimm.hpp:354-378).  cov_cut_off is -cc, min_reads is
+ * -mr (0: default). */
+int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads);
+
+/* Stage 3 - reassignment + LCA.  Replaces the read loop of filter_alignments
+ * (src/slimm.hpp:380-391, read_stat::update src/read_stat.hpp:98-114), slimm::get_lca
+ * (src/slimm.hpp:516-531) and phase 1 of get_reads_lca_count (:536-557).  Partial per rank: sum
+ * slimm_gpu_assign_device() across ranks (u32 words; the child marks are 0/1 counters). */
+int slimm_gpu_assign(slimm_gpu_ctx *ctx);
+int slimm_gpu_assign_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
+
+/* Convenience: coverage + filter + assign on one GPU. */
+int slimm_gpu_run(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads);
+
+/* ---- results (device -> caller-owned host buffers; any pointer may be NULL) ------------------- */
+int slimm_gpu_get_summary(slimm_gpu_ctx *ctx, slimm_gpu_summary *out);
+/* per reference [n_refs]: reference_contig members, src/reference_contig.hpp:100-127 */
+int slimm_gpu_get_ref_stats(slimm_gpu_ctx *ctx, uint32_t *reads_count, uint32_t *uniq_reads_count,
+                            uint32_t *uniq_reads_count2, uint32_t *nz_bins, uint32_t *uniq_nz_bins,
+                            float *cov_percent, float *uniq_cov_percent, uint8_t *valid);
+/* taxon_id__read_count after phase 1 as (taxon, count) sorted by taxon; taxon_id__children after
+ * phase 1 as distinct (taxon, ref) pairs sorted.  *n receives the number available; at most cap
+ * entries are written. */
+int slimm_gpu_get_lca_counts(slimm_gpu_ctx *ctx, uint32_t *taxon, uint32_t *count, uint64_t cap, uint64_t *n);
+int slimm_gpu_get_lca_children(slimm_gpu_ctx *ctx, uint32_t *taxon, uint32_t *ref, uint64_t cap, uint64_t *n);
+/* bins of one reference; which: 0 cov, 1 uniq_cov, 2 uniq_cov2 (needs SLIMM_GPU_KEEP_UNIQ_COV2).
+ * Replaces direct reads of bins_height in write_coverage / write_raw_stat (src/slimm.hpp:846-943). */
+int slimm_gpu_fetch_bins(slimm_gpu_ctx *ctx, int which, uint32_t ref, uint32_t *out, uint32_t cap);
+/* nonzero uniq_cov2 bins per reference (raw output column), needs SLIMM_GPU_KEEP_UNIQ_COV2 */
+int slimm_gpu_get_uniq2_nz(slimm_gpu_ctx *ctx, uint32_t *uniq2_nz_bins);
+/* per-read outcome (needs SLIMM_GPU_READ_RESULTS): for every read with >= 1 surviving target its id,
+ * kind (1: reassigned to a sole survivor, 2: LCA) and value (reference id or LCA taxon). */
+int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind, uint32_t *value,
+                           uint64_t cap, uint64_t *n);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF,
+       SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_COUNT };
+int slimm_gpu_enable_timing(slimm_gpu_ctx *ctx, int on);
+/* CUDA-event durations (ms) of the last run, per kernel group, and launches issued since create */
+int slimm_gpu_get_timings(slimm_gpu_ctx *ctx, float *ms, int n);
+int slimm_gpu_get_launch_count(slimm_gpu_ctx *ctx, uint64_t *n);
+
+/* ---- host-side tail of the path (no GPU needed) ---------------------------------------------- */
+/* Rank aggregation and abundances.  Replaces phases 2 and 3 of get_reads_lca_count
+ * (src/slimm.hpp:560-610) and the numeric part of write_abundance (:733-843). */
+typedef struct {
+    uint32_t taxon;        /* taxa_id column (without the '*')                                  */
+    uint32_t kind;         /* 0 plain row, 1 "<parent>*" unclassified row, 2 the final "0*" row  */
+    uint32_t read_count;
+    uint32_t first_child;  /* smallest contributing reference: its lineage names the row; ~0u for 0* */
+    double abundance;      /* f32 value for kinds 0/1, f64 for kind 2 (100.0 - float)            */
+} slimm_profile_row;
+
+typedef struct {
+    uint32_t n_refs;
+    const uint32_t *ref_len;           /* [n_refs]   */
+    const uint32_t *lineage;           /* [n_refs*8] */
+    uint64_t n_taxa;                   /* db.taxid__name restricted to what the caller has */
+    const uint32_t *taxa_id;           /* [n_taxa] */
+    const uint8_t *taxa_rank;          /* [n_taxa] 0..8 */
+    const uint8_t *taxa_has_name;      /* [n_taxa] name != "" */
+    uint64_t n_direct;                 /* slimm_gpu_get_lca_counts */
+    const uint32_t *direct_taxon, *direct_count;
+    uint64_t n_children;               /* slimm_gpu_get_lca_children */
+    const uint32_t *child_taxon, *child_ref;
+    const uint32_t *uniq_reads_count2; /* [n_refs] */
+    uint32_t matches_count, avg_read_length;
+    float coverage_cut_off, abundance_cut_off;
+    uint32_t rank;                     /* 1 species .. 6 phylum */
+} slimm_profile_input;
+
+/* rows: plain rows (ascending taxon), then "<parent>*" rows (ascending), then "0*".  Returns the
+ * number of rows through *n (at most cap written). */
+int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_row *rows, uint64_t cap, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIMM_GPU_H */

@@ -1,0 +1,46 @@
+"""CPU-side checks of the product library: it loads without a GPU, exports every symbol the header
+declares, refuses to run without a device (no fallback), and its host tail (slimm_profile_rows)
+reproduces the reference's _profile.tsv when fed the oracle's stage outputs."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import RANKS, all_runs, assert_profiles_match, load_case, runs_of
+from slimm_b200 import api, report
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    lib = api.load_library()
+    hdr = open(os.path.join(ROOT, "include", "slimm_gpu.h")).read()
+    declared = set(re.findall(r"\b(slimm_(?:gpu|profile)_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in slimm_gpu.h but not exported"
+    assert declared == set(api.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.SlimmGpuError):
+        api.SlimmGpu(np.array([1000], dtype=np.uint32), np.zeros((1, 8), dtype=np.uint32), 100, 100)
+
+
+@pytest.mark.parametrize("case_name,run_name", all_runs())
+def test_profile_rows_host_tail(case_name, run_name):
+    case = load_case(case_name)
+    run = [r for r in runs_of(case) if r.name == run_name][0]
+    w = run.bin_width or case.avg_read_length
+    res = oracle.run(case.ref_len, case.lineage, w, case.avg_read_length, run.cov_cut_off, case.read_id, case.ref_id,
+                     case.begin_pos, run.min_reads)
+    taxa = {t: (case.rank_of[t], case.name_of[t]) for t in case.rank_of}
+    rows = api.profile_rows(case.ref_len, case.lineage, taxa, res.direct, res.child_pairs, res.uniq_reads_count2,
+                            res.n_reads, case.avg_read_length, float(res.cut), run.abundance_cut_off, run.rank)
+    lines = report.profile_lines(rows, case.lineage, case.name_of, run.rank)
+    assert_profiles_match(os.path.join(run.path, "profile.tsv"), lines)
