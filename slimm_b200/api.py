@@ -313,17 +313,23 @@ class ProfileRow:
     abundance: float
 
 
-def profile_rows(ref_len, lineage, taxa: Dict[int, Tuple[int, str]], direct: Dict[int, int], children: np.ndarray,
-                 uniq_reads_count2, matches_count: int, avg_read_length: int, coverage_cut_off: float,
-                 abundance_cut_off: float = 0.01, rank: int = 1) -> List[ProfileRow]:
+def taxa_arrays(taxa: Dict[int, Tuple[int, str]]):
+    """taxid -> (rank, name) as the three arrays slimm_profile_rows takes."""
+    tid = np.fromiter(taxa.keys(), dtype=np.uint32, count=len(taxa))
+    trank = np.fromiter((v[0] for v in taxa.values()), dtype=np.uint8, count=len(taxa))
+    tname = np.fromiter((1 if v[1] != "" else 0 for v in taxa.values()), dtype=np.uint8, count=len(taxa))
+    return tid, trank, tname
+
+
+def profile_rows_arrays(ref_len, lineage, taxa_arr, direct: Dict[int, int], children: np.ndarray, uniq_reads_count2,
+                        matches_count: int, avg_read_length: int, coverage_cut_off: float,
+                        abundance_cut_off: float = 0.01, rank: int = 1) -> List[ProfileRow]:
     """Host tail of the path: rank aggregation + abundances (slimm_profile_rows; replaces reference
     src/slimm.hpp:560-610 and the numeric part of :733-843)."""
     lib = load_library()
     ref_len = np.ascontiguousarray(ref_len, dtype=np.uint32)
     lineage = np.ascontiguousarray(lineage, dtype=np.uint32)
-    tid = np.fromiter(taxa.keys(), dtype=np.uint32, count=len(taxa))
-    trank = np.fromiter((v[0] for v in taxa.values()), dtype=np.uint8, count=len(taxa))
-    tname = np.fromiter((1 if v[1] != "" else 0 for v in taxa.values()), dtype=np.uint8, count=len(taxa))
+    tid, trank, tname = taxa_arr
     dt = np.fromiter(direct.keys(), dtype=np.uint32, count=len(direct))
     dc = np.fromiter(direct.values(), dtype=np.uint32, count=len(direct))
     ch = np.ascontiguousarray(children, dtype=np.uint32).reshape(-1, 2)
@@ -334,9 +340,28 @@ def profile_rows(ref_len, lineage, taxa: Dict[int, Tuple[int, str]], direct: Dic
                         ct.ctypes.data, cr.ctypes.data, u2.ctypes.data, matches_count, avg_read_length,
                         coverage_cut_off, abundance_cut_off, rank)
     n = C.c_uint64()
-    cap = 2 * len(taxa) + 8
+    cap = 2 * int(tid.size) + 8
     rows = (_Row * cap)()
     rc = lib.slimm_profile_rows(C.byref(inp), rows, cap, C.byref(n))
     if rc != 0:
         raise SlimmGpuError(f"slimm_profile_rows: {lib.slimm_gpu_strerror(rc).decode()}")
     return [ProfileRow(r.taxon, r.kind, r.read_count, r.first_child, r.abundance) for r in rows[: n.value]]
+
+
+def profile_rows(ref_len, lineage, taxa: Dict[int, Tuple[int, str]], direct, children, uniq_reads_count2,
+                 matches_count: int, avg_read_length: int, coverage_cut_off: float,
+                 abundance_cut_off: float = 0.01, rank: int = 1) -> List[ProfileRow]:
+    return profile_rows_arrays(ref_len, lineage, taxa_arrays(taxa), direct, children, uniq_reads_count2,
+                               matches_count, avg_read_length, coverage_cut_off, abundance_cut_off, rank)
+
+
+class _DevicePointer:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_tensor(ptr: int, n: int, dtype, device):
+    """Zero-copy torch view of library-owned device memory (for NCCL reductions across ranks)."""
+    import torch
+    typestr = {torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevicePointer(ptr, n, typestr), device=device)

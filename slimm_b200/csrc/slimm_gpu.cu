@@ -745,7 +745,6 @@ static int zero_state(slimm_gpu_ctx *ctx)
     CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
     if (ctx->d_cov2) CU(cudaMemsetAsync(ctx->d_cov2, 0, std::max<u64>(ctx->Bp, 64) * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
-    ctx->launches += 2 + (ctx->d_cov2 != nullptr);
     return SLIMM_GPU_OK;
 }
 
@@ -771,7 +770,7 @@ static int sort_records(slimm_gpu_ctx *ctx)
     CU(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ctx->d_rid, ctx->d_rid_sorted, (const u64 *)packed,
                                                     (u64 *)ctx->d_rp_sorted, n, 0, 32, ctx->stream);
-    ctx->launches += 8;
+    ctx->launches += 1;   // k_pack_values; the CUB sort kernels are library code and not counted
     cudaStreamSynchronize(ctx->stream);
     cudaFree(tmp); cudaFree(packed);
     if (e != cudaSuccess) { ctx->err = std::string("cub radix sort failed: ") + cudaGetErrorString(e); return SLIMM_GPU_ECUDA; }
@@ -846,7 +845,7 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
         const u64 n_chunks = (n_steps + STATS_STEPS_PER_WARP - 1) / STATS_STEPS_PER_WARP;
         const int grid = grid_for(ctx, n_chunks * 32, 256, 8);
         if (n_steps) k_ref_stats<<<grid, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, n_steps, ctx->d_off, ctx->G, ctx->d_stats);
-        ctx->launches += 2;
+        ctx->launches += 1;
         CU(cudaGetLastError());
     }
     {
@@ -875,7 +874,6 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     TimeScope ts(ctx, SLIMM_GPU_T_ASSIGN);
     CU(cudaMemsetAsync(ctx->d_assign, 0, ctx->assign_words * 4, ctx->stream));
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
-    ctx->launches++;
     if (ctx->n) {
         u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
         const int grid = grid_for(ctx, ctx->n, 256, 8);
