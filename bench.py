@@ -126,11 +126,8 @@ def make_community(wl):
 
 def profile_tail(api, gpu, contigs, lineage, taxa_arrays, cc):
     """D2H of the stage results + host rank aggregation (the 'profile' end of the path)."""
-    s = gpu.summary()
-    st_u2 = gpu.ref_stats().uniq_reads_count2
-    rows = api.profile_rows_arrays(contigs.lengths, lineage, taxa_arrays, gpu.lca_counts(), gpu.lca_children(), st_u2,
-                                   s.matches_count, AVG_READ_LEN, s.coverage_cut_off, 0.01, 1)
-    return s, rows
+    rows, n_rows = gpu.profile_raw(1, 0.01)      # slimm_gpu_profile: result readback + rank aggregation
+    return gpu.summary(), n_rows
 
 
 def run_reference_sample(wl, n_sample, steps, warmup, tmp_root=None):
@@ -255,6 +252,7 @@ def main():
     gpu = api.SlimmGpu(contigs.lengths, lineage, wl["w"], AVG_READ_LEN, device=local_rank)
     gpu.set_stream(stream.cuda_stream)
     gpu.enable_timing(True)
+    gpu.set_taxa(taxa_arrays)
     flush = None if wl["N"] * 12 > 400e6 else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def allreduce_ptr(ptr, n_words, dtype=torch.int32):
@@ -320,12 +318,14 @@ def main():
     P, U, B = summ.n_pairs, summ.uniq_matches_count, summ.n_bins
     if world > 1:   # this rank's share of the pairs / unique reads
         P, U = P / world, U / world
-    cov_ms = statistics.mean(k["coverage"] for k in ktimes)
+    kernel_ms = {k: statistics.mean(t[k] for t in ktimes) for k in ktimes[0]}
+    # coverage = bucket count + emit + accumulate when the bucketed scatter is used, one kernel otherwise
+    cov_ms = kernel_ms["bucket_count"] + kernel_ms["coverage"] + kernel_ms["accumulate"]
     cov_bytes = 16.0 * n_local + 8.0 * P + 8.0 * U
     achieved = cov_bytes / (cov_ms * 1e-3) / 1e9
     pipe_bytes = 32.0 * n_local + 8.0 * P + 8.0 * U + 16.0 * B
-    kernel_ms = {k: statistics.mean(t[k] for t in ktimes) for k in ktimes[0]}
-    roofline = {"bound": "hbm", "kernel": "k_coverage", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "coverage scatter (k_bucket_count + k_coverage + k_accumulate)"
+                if kernel_ms["accumulate"] > 0 else "k_coverage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": cov_bytes, "kernel_ms": cov_ms,
                 "pipeline": {"algorithmic_bytes_per_step": pipe_bytes, "ms_per_step": ms_per_step,
@@ -368,7 +368,7 @@ def main():
         line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": int(launches),
                      "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                      "result": {"hits": summ.hits_count, "reads": summ.matches_count, "uniq": summ.uniq_matches_count,
-                                "uniq2": summ.uniq_matches_count2, "valid_refs": summ.n_valid, "rows": len(rows),
+                                "uniq2": summ.uniq_matches_count2, "valid_refs": summ.n_valid, "rows": rows,
                                 "pairs": summ.n_pairs, "bins": summ.n_bins, "sorted_input": summ.input_was_sorted}})
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -159,12 +159,16 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
                            uint64_t cap, uint64_t *n);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
-enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF,
-       SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_COUNT };
+enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_BCOUNT, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_ACCUM,
+       SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF, SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_COUNT };
 int slimm_gpu_enable_timing(slimm_gpu_ctx *ctx, int on);
 /* CUDA-event durations (ms) of the last run, per kernel group, and launches issued since create */
 int slimm_gpu_get_timings(slimm_gpu_ctx *ctx, float *ms, int n);
 int slimm_gpu_get_launch_count(slimm_gpu_ctx *ctx, uint64_t *n);
+
+/* Scatter strategy of the coverage stage: -1 automatic (bucketed multisplit when the histogram is much
+ * larger than L2), 0 direct global REDs, 1 bucketed.  Results are identical; tests force both. */
+int slimm_gpu_set_scatter_mode(slimm_gpu_ctx *ctx, int mode);
 
 /* ---- host-side tail of the path (no GPU needed) ---------------------------------------------- */
 /* Rank aggregation and abundances.  Replaces phases 2 and 3 of get_reads_lca_count
@@ -198,6 +202,14 @@ typedef struct {
 /* rows: plain rows (ascending taxon), then "<parent>*" rows (ascending), then "0*".  Returns the
  * number of rows through *n (at most cap written). */
 int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_row *rows, uint64_t cap, uint64_t *n);
+
+/* The same tail fed straight from the context (no intermediate taxon lists): slimm_gpu_set_taxa once per
+ * database (db.taxid__name: rank 0..8 and whether the name is non-empty), then slimm_gpu_profile after
+ * slimm_gpu_assign.  Replaces the calls at reference src/slimm.hpp:485 (phases 2-3) and :489 (numbers). */
+int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa_id, const uint8_t *taxa_rank,
+                       const uint8_t *taxa_has_name);
+int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off, slimm_profile_row *rows,
+                      uint64_t cap, uint64_t *n);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libslimm_gpu.so")
 
 KEEP_UNIQ_COV2 = 1
 READ_RESULTS = 2
-TIMING_NAMES = ["sort", "zero", "coverage", "stats", "cutoff", "assign"]
+TIMING_NAMES = ["sort", "zero", "bucket_count", "coverage", "accumulate", "stats", "cutoff", "assign"]
 
 EXPORTED_SYMBOLS = [
     "slimm_gpu_strerror", "slimm_gpu_last_error", "slimm_gpu_device_count", "slimm_gpu_create", "slimm_gpu_destroy",
@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "slimm_gpu_assign_device", "slimm_gpu_run", "slimm_gpu_get_summary", "slimm_gpu_get_ref_stats",
     "slimm_gpu_get_lca_counts", "slimm_gpu_get_lca_children", "slimm_gpu_fetch_bins", "slimm_gpu_get_uniq2_nz",
     "slimm_gpu_read_results", "slimm_gpu_enable_timing", "slimm_gpu_get_timings", "slimm_gpu_get_launch_count",
-    "slimm_profile_rows",
+    "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
 ]
 
 
@@ -110,6 +110,9 @@ def load_library():
     lib.slimm_gpu_get_timings.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.slimm_gpu_get_launch_count.argtypes = [vp, C.POINTER(u64)]
     lib.slimm_profile_rows.argtypes = [C.POINTER(_ProfileInput), C.POINTER(_Row), u64, C.POINTER(u64)]
+    lib.slimm_gpu_set_scatter_mode.argtypes = [vp, C.c_int]
+    lib.slimm_gpu_set_taxa.argtypes = [vp, u64, vp, vp, vp]
+    lib.slimm_gpu_profile.argtypes = [vp, u32, C.c_float, C.POINTER(_Row), u64, C.POINTER(u64)]
     _lib = lib
     return lib
 
@@ -288,6 +291,30 @@ class SlimmGpu:
         self._check(self._lib.slimm_gpu_read_results(self._ctx, rid.ctypes.data, kind.ctypes.data, val.ctypes.data,
                                                      n.value, C.byref(n)), "read_results")
         return rid, kind, val
+
+    # -- profile tail -------------------------------------------------------------------------
+    def set_taxa(self, taxa):
+        """``taxa``: dict taxid -> (rank, name) (db.taxid__name) or the arrays from :func:`taxa_arrays`."""
+        tid, trank, tname = taxa_arrays(taxa) if isinstance(taxa, dict) else taxa
+        self._taxa_keep = (tid, trank, tname)
+        self._rows_cap = 2 * int(tid.size) + 8
+        self._rows_buf = (_Row * self._rows_cap)()
+        self._check(self._lib.slimm_gpu_set_taxa(self._ctx, tid.size, tid.ctypes.data, trank.ctypes.data,
+                                                 tname.ctypes.data), "set_taxa")
+
+    def profile_raw(self, rank: int = 1, abundance_cut_off: float = 0.01):
+        """Rank aggregation + abundances straight from the device results; returns (ctypes rows, n)."""
+        n = C.c_uint64()
+        self._check(self._lib.slimm_gpu_profile(self._ctx, rank, abundance_cut_off, self._rows_buf, self._rows_cap,
+                                                C.byref(n)), "profile")
+        return self._rows_buf, n.value
+
+    def profile(self, rank: int = 1, abundance_cut_off: float = 0.01) -> List["ProfileRow"]:
+        rows, n = self.profile_raw(rank, abundance_cut_off)
+        return [ProfileRow(r.taxon, r.kind, r.read_count, r.first_child, r.abundance) for r in rows[:n]]
+
+    def set_scatter_mode(self, mode: int):
+        self._check(self._lib.slimm_gpu_set_scatter_mode(self._ctx, mode), "set_scatter_mode")
 
     # -- instrumentation ----------------------------------------------------------------------
     def enable_timing(self, on: bool = True):

@@ -1,159 +1,174 @@
 // profile_host.cpp - host tail of the hot path: rank aggregation + abundances.
 //
 // Replaces phases 2 and 3 of slimm::get_reads_lca_count (reference src/slimm.hpp:560-610) and the
-// numeric part of slimm::write_abundance (:733-843).  O(G + T) work on the arrays the GPU stages
-// produced; the text formatting (lineage strings, TSV) stays with the caller.
+// numeric part of slimm::write_abundance (:733-843).  O(G + T) work on what the GPU stages produced;
+// text formatting (lineage strings, TSV) stays with the caller.
 //
-// Sets of contributing references are kept as sorted vectors that are merged lazily; the reference
-// uses std::set<uint32_t> per taxon.  The reference walks its snapshot of direct counts in
-// libstdc++ hash order; here the order is ascending (rank, taxon) - identical results whenever the
-// lineage table is tree-consistent.
+// The reference keeps unordered_map<taxon, count> and unordered_map<taxon, std::set<ref>>.  Here every
+// taxon that can occur is a value of the [G,8] lineage table, so a plan built once per database maps
+// lineage slots to dense taxon indices and all per-sample state lives in flat arrays; sets of
+// contributing references are sorted vectors merged lazily, and only collected for taxa whose set is
+// ever read (taxa with direct counts, the requested rank and its parent rank, strain level).
+// The reference walks its snapshot of direct counts in libstdc++ hash order; here the order is
+// ascending (rank, taxon) - identical results whenever the lineage table is tree-consistent
+// (SURVEY.md appendix A8).
+#include "profile_host.h"
+
 #include <algorithm>
-#include <cstdint>
-#include <unordered_map>
-#include <vector>
+#include <cstring>
 
-#include "../../include/slimm_gpu.h"
+namespace slimm_host {
 
-namespace {
-
-typedef uint32_t u32;
-typedef uint64_t u64;
-
-struct Node {
-    u32 count = 0;
-    bool has_count = false;
-    bool dirty = false;
-    std::vector<u32> kids;   // taxon_id__children[t]
-    void add_count(u32 c) { count += c; has_count = true; }   // u32 wrap as increment_or_initialize
-    void normalize()
-    {
-        if (!dirty) return;
-        std::sort(kids.begin(), kids.end());
-        kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
-        dirty = false;
-    }
-};
-
-struct TaxInfo { uint8_t rank = 0; uint8_t has_name = 0; };
-
-}  // namespace
-
-extern "C" int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_row *rows, uint64_t cap, uint64_t *n_out)
+ProfilePlan::ProfilePlan(u32 n_refs, const u32 *ref_len, const u32 *lineage, u64 n_taxa, const u32 *taxa_id,
+                         const uint8_t *taxa_rank, const uint8_t *taxa_has_name)
+    : G(n_refs), len(ref_len, ref_len + n_refs), lin(lineage, lineage + (size_t)n_refs * 8)
 {
-    if (!in || !n_out || in->rank < 1 || in->rank > 6 || !in->lineage || !in->ref_len) return SLIMM_GPU_EINVAL;
-    const u32 G = in->n_refs;
-    const u32 *lin = in->lineage;
-    std::unordered_map<u32, TaxInfo> info;
-    info.reserve(in->n_taxa * 2 + 16);
-    for (u64 i = 0; i < in->n_taxa; ++i) {
-        TaxInfo ti;
-        ti.rank = in->taxa_rank[i];
-        ti.has_name = in->taxa_has_name[i];
-        info[in->taxa_id[i]] = ti;
+    vals = lin;
+    std::sort(vals.begin(), vals.end());
+    vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+    const size_t T = vals.size();
+    slot_t.resize(lin.size());
+    for (size_t s = 0; s < lin.size(); ++s) slot_t[s] = (u32)(std::lower_bound(vals.begin(), vals.end(), lin[s]) - vals.begin());
+    rank.assign(T, 0);   // db.taxid__name[t] default-inserts (strain_lv, "") for unknown taxa
+    named.assign(T, 0);
+    for (u64 i = 0; i < n_taxa; ++i) {
+        auto it = std::lower_bound(vals.begin(), vals.end(), taxa_id[i]);
+        if (it != vals.end() && *it == taxa_id[i]) {
+            rank[it - vals.begin()] = taxa_rank[i];
+            named[it - vals.begin()] = taxa_has_name[i];
+        }
     }
-    auto rank_of = [&](u32 t) -> u32 { auto it = info.find(t); return it == info.end() ? 0u : it->second.rank; };
-    auto has_name = [&](u32 t) -> bool { auto it = info.find(t); return it != info.end() && it->second.has_name; };
+    count.assign(T, 0); direct.assign(T, 0); has_count.assign(T, 0); dirty.assign(T, 0); seen.assign(T, 0);
+    kids.resize(T);
+    pab.assign(T, 0.0f); sab.assign(T, 0.0f); pcnt.assign(T, 0); scnt.assign(T, 0); has_p.assign(T, 0); has_s.assign(T, 0);
+}
 
-    std::unordered_map<u32, Node> nodes;
-    nodes.reserve(in->n_direct * 4 + (u64)G + 64);
-    // phase 1 results from the GPU (src/slimm.hpp:536-557)
-    for (u64 i = 0; i < in->n_direct; ++i) nodes[in->direct_taxon[i]].add_count(in->direct_count[i]);
-    for (u64 i = 0; i < in->n_children; ++i) {
-        if (in->child_ref[i] >= G) return SLIMM_GPU_EINVAL;
-        Node &nd = nodes[in->child_taxon[i]];
-        nd.kids.push_back(in->child_ref[i]);
-        nd.dirty = true;
+int ProfilePlan::find(u32 taxon) const
+{
+    auto it = std::lower_bound(vals.begin(), vals.end(), taxon);
+    return (it != vals.end() && *it == taxon) ? (int)(it - vals.begin()) : -1;
+}
+
+void ProfilePlan::touch(u32 t)
+{
+    if (!seen[t]) { seen[t] = 1; touched.push_back(t); }
+}
+
+void ProfilePlan::normalize(u32 t)
+{
+    if (!dirty[t]) return;
+    std::vector<u32> &k = kids[t];
+    std::sort(k.begin(), k.end());
+    k.erase(std::unique(k.begin(), k.end()), k.end());
+    dirty[t] = 0;
+}
+
+void ProfilePlan::begin()
+{
+    for (u32 t : touched) {
+        count[t] = 0; direct[t] = 0; has_count[t] = 0; dirty[t] = 0; seen[t] = 0; kids[t].clear();
+        pab[t] = sab[t] = 0.0f; pcnt[t] = scnt[t] = 0; has_p[t] = has_s[t] = 0;
     }
+    touched.clear();
+    snapshot.clear();
+}
+
+void ProfilePlan::add_direct(u32 t, u32 c)
+{
+    touch(t);
+    if (!direct[t] && c) snapshot.push_back(t);
+    count[t] += c; direct[t] += c; has_count[t] = 1;   // increment_or_initialize (src/misc.hpp:138-147)
+}
+
+void ProfilePlan::add_child(u32 t, u32 ref)
+{
+    touch(t);
+    std::vector<u32> &k = kids[t];
+    if (!k.empty() && k.back() > ref) dirty[t] = 1;
+    if (k.empty() || k.back() != ref) k.push_back(ref);
+}
+
+int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
+                        float abundance_cut_off, u32 rk, std::vector<slimm_profile_row> &out)
+{
+    out.clear();
+    if (rk < 1 || rk > 6) return SLIMM_GPU_EINVAL;
+    const u32 pr = rk + 1;
+    // a taxon's reference set is only ever read if it has a direct count (phase 2 reads it live), is at the
+    // requested rank or its parent rank (write_abundance) or at strain level (phase 3 reads children[lineage[0]])
+    auto need_kids = [&](u32 t) { return direct[t] != 0 || rank[t] == rk || rank[t] == pr || rank[t] == 0; };
     // phase 2 (:560-586): push each direct count and its children up the first child's lineage
-    std::vector<std::pair<u32, u32>> snapshot;   // (taxon, count)
-    snapshot.reserve(in->n_direct);
-    for (u64 i = 0; i < in->n_direct; ++i) snapshot.emplace_back(in->direct_taxon[i], in->direct_count[i]);
-    std::sort(snapshot.begin(), snapshot.end(), [&](const std::pair<u32, u32> &a, const std::pair<u32, u32> &b) {
-        u32 ra = rank_of(a.first), rb = rank_of(b.first);
-        return ra != rb ? ra < rb : a.first < b.first;
-    });
-    std::vector<u32> kids;
-    for (auto &tc : snapshot) {
-        Node &nd = nodes[tc.first];
-        nd.normalize();
-        if (nd.kids.empty()) return SLIMM_GPU_EINVAL;           // .at() would throw in the reference
-        kids = nd.kids;                                          // copied before the loop (:575)
-        const u32 f = kids[0];
-        for (u32 j = rank_of(tc.first) + 1; j < 8; ++j) {
-            Node &rc = nodes[lin[(u64)f * 8 + j]];               // may rehash: nd is not used below
-            rc.add_count(tc.second);
-            rc.kids.insert(rc.kids.end(), kids.begin(), kids.end());
-            rc.dirty = true;
+    std::sort(snapshot.begin(), snapshot.end(), [&](u32 a, u32 b) { return rank[a] != rank[b] ? rank[a] < rank[b] : a < b; });
+    std::vector<u32> tmp;
+    for (u32 t : snapshot) {
+        normalize(t);
+        if (kids[t].empty()) return SLIMM_GPU_EINVAL;            // .at() would throw in the reference
+        tmp = kids[t];                                           // copied before the loop (:575)
+        const u32 f = tmp[0], c = direct[t];
+        for (u32 j = rank[t] + 1; j < 8; ++j) {
+            const u32 rc = slot_t[(size_t)f * 8 + j];
+            touch(rc);
+            count[rc] += c; has_count[rc] = 1;
+            if (need_kids(rc)) { kids[rc].insert(kids[rc].end(), tmp.begin(), tmp.end()); dirty[rc] = 1; }
         }
     }
     // phase 3 (:589-610): uniquely (re)assigned reads up each reference's own lineage
     for (u32 g = 0; g < G; ++g) {
-        const u32 u2 = in->uniq_reads_count2 ? in->uniq_reads_count2[g] : 0;
+        const u32 u2 = uniq_reads_count2 ? uniq_reads_count2[g] : 0;
         if (u2 == 0) continue;
-        Node &n0 = nodes[lin[(u64)g * 8]];                       // default-inserted like operator[]
-        n0.normalize();
-        kids = n0.kids;
+        const u32 t0 = slot_t[(size_t)g * 8];
+        normalize(t0);
+        const std::vector<u32> k0 = kids[t0];                      // copied once before the loop (:594)
         for (u32 j = 1; j < 8; ++j) {
-            Node &rc = nodes[lin[(u64)g * 8 + j]];
-            rc.add_count(u2);
-            rc.kids.push_back(g);
-            rc.kids.insert(rc.kids.end(), kids.begin(), kids.end());
-            rc.dirty = true;
+            const u32 rc = slot_t[(size_t)g * 8 + j];
+            touch(rc);
+            count[rc] += u2; has_count[rc] = 1;
+            if (need_kids(rc)) {
+                std::vector<u32> &k = kids[rc];
+                k.push_back(g);
+                k.insert(k.end(), k0.begin(), k0.end());
+                dirty[rc] = 1;
+            }
         }
     }
-
-    // write_abundance (:733-843)
-    const u32 rk = in->rank, pr = in->rank + 1;
-    const float R = (float)in->matches_count;
-    std::vector<u32> taxa;
-    taxa.reserve(nodes.size());
-    for (auto &kv : nodes)
-        if (kv.second.has_count) taxa.push_back(kv.first);
-    std::sort(taxa.begin(), taxa.end());
-    std::unordered_map<u32, float> pab, sab;
-    std::unordered_map<u32, u32> pcnt, scnt;
-    for (u32 t : taxa)
-        if (rank_of(t) == pr) {
-            const Node &nd = nodes[t];
-            pab[t] = (float)nd.count / R * 100;                   // float(c)/(matches_count) * 100
-            pcnt[t] = nd.count;
-        }
-    std::vector<slimm_profile_row> out;
+    // write_abundance (:733-843); rows in ascending taxon order
+    std::sort(touched.begin(), touched.end());
+    const float R = (float)matches_count;
+    for (u32 t : touched)
+        if (has_count[t] && rank[t] == pr) { pab[t] = (float)count[t] / R * 100; pcnt[t] = count[t]; has_p[t] = 1; }
     std::vector<u32> parents;
     float sum_ab = 0.0f;
     u32 sum_cnt = 0;
-    for (u32 t : taxa) {
-        if (rank_of(t) != rk) continue;
-        Node &nd = nodes[t];
-        nd.normalize();
-        if (nd.kids.empty()) return SLIMM_GPU_EINVAL;
+    const size_t n_touched = touched.size();   // touch() below may append parents: iterate the fixed prefix
+    for (size_t ti = 0; ti < n_touched; ++ti) {
+        const u32 t = touched[ti];
+        if (!has_count[t] || rank[t] != rk) continue;
+        normalize(t);
+        const std::vector<u32> &k = kids[t];
+        if (k.empty()) return SLIMM_GPU_EINVAL;
         u32 gl = 0;
-        for (u32 k : nd.kids) gl += in->ref_len[k];                // u32 wrap (:785)
-        gl /= (u32)nd.kids.size();
-        const float cov = (float)(u32)(nd.count * in->avg_read_length) / gl;   // u32 product (:792)
-        const float ab = (float)nd.count / R * 100;
-        const u32 p = lin[(u64)nd.kids.back() * 8 + pr];           // lineage of the last child iterated
-        if (sab.find(p) == sab.end()) { sab[p] = ab; scnt[p] = nd.count; parents.push_back(p); }
-        else { sab[p] += ab; scnt[p] += nd.count; }
-        if (ab < in->abundance_cut_off || cov < in->coverage_cut_off || !has_name(t)) continue;
+        for (u32 r : k) gl += len[r];                              // u32 wrap (:785)
+        gl /= (u32)k.size();
+        const float cov = (float)(u32)(count[t] * avg_read_length) / gl;   // u32 product (:792)
+        const float ab = (float)count[t] / R * 100;
+        const u32 p = slot_t[(size_t)k.back() * 8 + pr];           // lineage of the last child iterated
+        if (!has_s[p]) { has_s[p] = 1; sab[p] = ab; scnt[p] = count[t]; parents.push_back(p); touch(p); }
+        else { sab[p] += ab; scnt[p] += count[t]; }
+        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) continue;
         slimm_profile_row r;
-        r.taxon = t; r.kind = 0; r.read_count = nd.count; r.first_child = nd.kids[0]; r.abundance = ab;
+        r.taxon = vals[t]; r.kind = 0; r.read_count = count[t]; r.first_child = k[0]; r.abundance = ab;
         out.push_back(r);
         sum_ab += ab;
-        sum_cnt += nd.count;
+        sum_cnt += count[t];
     }
     std::sort(parents.begin(), parents.end());
     for (u32 p : parents) {
-        auto pa = pab.find(p);
-        const float uab = (pa == pab.end() ? 0.0f : pa->second) - sab[p];
-        auto pc = pcnt.find(p);
-        const u32 ucnt = (pc == pcnt.end() ? 0u : pc->second) - scnt[p];
-        if (uab > in->abundance_cut_off && has_name(p)) {
+        const float uab = (has_p[p] ? pab[p] : 0.0f) - sab[p];
+        const u32 ucnt = (has_p[p] ? pcnt[p] : 0u) - scnt[p];
+        if (uab > abundance_cut_off && named[p]) {
             slimm_profile_row r;
-            r.taxon = p; r.kind = 1; r.read_count = ucnt; r.abundance = uab; r.first_child = 0xFFFFFFFFu;
-            auto it = nodes.find(p);
-            if (p != 0 && it != nodes.end()) { it->second.normalize(); if (!it->second.kids.empty()) r.first_child = it->second.kids[0]; }
+            r.taxon = vals[p]; r.kind = 1; r.read_count = ucnt; r.abundance = uab; r.first_child = 0xFFFFFFFFu;
+            if (vals[p] != 0) { normalize(p); if (!kids[p].empty()) r.first_child = kids[p][0]; }
             out.push_back(r);
             sum_cnt += ucnt;
             sum_ab += uab;
@@ -162,10 +177,34 @@ extern "C" int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_r
     slimm_profile_row last;
     last.taxon = 0; last.kind = 2; last.first_child = 0xFFFFFFFFu;
     last.abundance = 100.0 - sum_ab;                               // double minus float (:835)
-    last.read_count = in->matches_count - sum_cnt;                 // u32 wrap
+    last.read_count = matches_count - sum_cnt;                     // u32 wrap
     out.push_back(last);
+    return SLIMM_GPU_OK;
+}
+
+}  // namespace slimm_host
+
+extern "C" int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_row *rows, uint64_t cap, uint64_t *n_out)
+{
+    if (!in || !n_out || in->rank < 1 || in->rank > 6 || !in->lineage || !in->ref_len) return SLIMM_GPU_EINVAL;
+    slimm_host::ProfilePlan plan(in->n_refs, in->ref_len, in->lineage, in->n_taxa, in->taxa_id, in->taxa_rank, in->taxa_has_name);
+    plan.begin();
+    for (uint64_t i = 0; i < in->n_direct; ++i) {
+        int t = plan.find(in->direct_taxon[i]);
+        if (t < 0) return SLIMM_GPU_EINVAL;
+        plan.add_direct((uint32_t)t, in->direct_count[i]);
+    }
+    for (uint64_t i = 0; i < in->n_children; ++i) {
+        int t = plan.find(in->child_taxon[i]);
+        if (t < 0 || in->child_ref[i] >= in->n_refs) return SLIMM_GPU_EINVAL;
+        plan.add_child((uint32_t)t, in->child_ref[i]);
+    }
+    std::vector<slimm_profile_row> out;
+    int rc = plan.finish(in->uniq_reads_count2, in->matches_count, in->avg_read_length, in->coverage_cut_off,
+                         in->abundance_cut_off, in->rank, out);
+    if (rc) return rc;
     *n_out = out.size();
-    for (u64 i = 0; i < out.size() && i < cap; ++i)
+    for (uint64_t i = 0; i < out.size() && i < cap; ++i)
         if (rows) rows[i] = out[i];
     return SLIMM_GPU_OK;
 }

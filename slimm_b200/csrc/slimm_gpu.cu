@@ -1,451 +1,20 @@
-// slimm_gpu.cu - sm_100a kernels + C ABI of the SLIMM profiling hot path (see include/slimm_gpu.h).
-//
-// Data layout in HBM (DESIGN.md has the long form):
-//   records   : struct-of-arrays  read_id[N] u32 | ref_id[N] u32 | begin_pos[N] i32, in file order
-//               (or, after the device sort of unsorted input, read_id[N] + packed {ref,pos}[N] u64)
-//   ref_meta  : uint4[G] = {len, nb = len/w+1, bin offset lo, hi}; offsets are padded to 64 bins so
-//               every 512-byte warp step of the stats kernel belongs to one reference
-//   hist      : u64[Bp]  = {lo: cov bin, hi: uniq_cov bin} interleaved, one 64-bit RED per pair
-//   cov2      : u32[Bp]  uniq_cov2 (only with SLIMM_GPU_KEEP_UNIQ_COV2)
-//   stats     : u32[G*4] = {nz, reads_count, uniq nz, uniq_reads_count}
-//   assign    : u32[(17+T)*G] = uniq_reads_count2[G] | lca_count[G*8] | child_mark[G*8] | fb_mark[T*G]
-//               keyed by (reference, lineage level) instead of taxon id, so no device hash map
-//
-// Every kernel here is HBM / L2-atomic bound integer work: no tensor cores, no CPU fallback.
+// slimm_gpu.cu - C ABI of the SLIMM profiling hot path (see include/slimm_gpu.h); the kernels live in
+// kernels.cuh, the host tail (rank aggregation) in profile_host.cpp.  There is no CPU fallback.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/slimm_gpu.h"
-
-typedef uint32_t u32;
-typedef uint64_t u64;
-typedef int32_t i32;
-
-// ------------------------------------------------------------------------------------------------
-// device-side scalars
-// ------------------------------------------------------------------------------------------------
-struct DevScalars {
-    unsigned long long n_reads;   // matches_count   (partial per rank)      } summed across ranks
-    unsigned long long n_uniq;    // uniq_matches_count                      } by the caller
-    unsigned long long n_uniq2;   // uniq_matches_count2
-    unsigned long long n_pairs;   // sum of reads_count
-    u32 flags;                    // bit0: read ids not non-decreasing, bit1: ref_id >= G
-    u32 n_valid, failed_cov, failed_ucov, failed_minread, ref_count;
-    float cut, ucut;
-    u32 done_ctr;
-    u32 pad;
-};
-
-// record accessors: plain SoA, or {read_id[], packed (ref | pos<<32)[]} after the device sort
-struct RecSoA {
-    const u32 *rid; const u32 *ref; const i32 *pos;
-    __device__ __forceinline__ u32 read(u64 i) const { return __ldg(rid + i); }
-    __device__ __forceinline__ u32 refid(u64 i) const { return __ldg(ref + i); }
-    __device__ __forceinline__ u32 upos(u64 i) const { return (u32)__ldg(pos + i); }
-};
-struct RecPacked {
-    const u32 *rid; const uint2 *rp;
-    __device__ __forceinline__ u32 read(u64 i) const { return __ldg(rid + i); }
-    __device__ __forceinline__ u32 refid(u64 i) const { return __ldg(&rp[i].x); }
-    __device__ __forceinline__ u32 upos(u64 i) const { return __ldg(&rp[i].y); }
-};
-
-__device__ __forceinline__ u32 warp_sum(u32 v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// one atomic per distinct key per warp; must be reached by all 32 lanes
-__device__ __forceinline__ void warp_agg_add(u32 *base, u32 key, bool active)
-{
-    unsigned act = __ballot_sync(0xffffffffu, active);
-    if (active) {
-        unsigned peers = __match_any_sync(act, key);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(base + key, (u32)__popc(peers));
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: coverage.  One thread per record.  Replaces reference src/slimm.hpp:194-257 +
-// src/read_stat.hpp:116-135: a record contributes iff it is the first of its (read, ref) pair in
-// file order; a read is unique iff all its records name one reference.  Reads are runs of equal
-// read_id (input is non-decreasing in read_id, checked here: bit0 of flags).
-// ------------------------------------------------------------------------------------------------
-template <class Rec>
-__global__ void __launch_bounds__(256)
-k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, u32 w,
-           unsigned long long *__restrict__ hist, DevScalars *sc)
-{
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u32 heads = 0, uniq = 0, bad = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u32 r = rec.read(i), g = rec.refid(i);
-        if (g >= G) { bad |= 2u; continue; }
-        bool head = true, first = true, multi = false;
-        if (i > 0) {
-            u32 pr = rec.read(i - 1);
-            if (pr > r) bad |= 1u;
-            head = pr != r;
-        }
-        if (!head) {                       // look back over the run for an earlier hit of (read, g)
-            u64 j = i;
-            while (j > 0 && rec.read(j - 1) == r) {
-                --j;
-                if (rec.refid(j) == g) { first = false; break; }
-                multi = true;
-            }
-        }
-        if (!first) continue;              // repeat hit: dropped (src/read_stat.hpp:125-131)
-        if (!multi) {                      // look ahead: does the read name any other reference?
-            u64 j = i + 1;
-            while (j < n && rec.read(j) == r) {
-                if (rec.refid(j) != g) { multi = true; break; }
-                ++j;
-            }
-        }
-        if (head) { ++heads; uniq += !multi; }
-        const uint4 m = __ldg(meta + g);   // {len, nb, off_lo, off_hi}
-        u32 center = rec.upos(i) + half_avg;          // u32 wrap as in src/slimm.hpp:200
-        center = min(center, m.x);
-        const u64 b = (((u64)m.w << 32) | m.z) + center / w;
-        atomicAdd(hist + b, multi ? 1ull : 0x100000001ull);   // cov += 1 [, uniq_cov += 1]
-    }
-    heads = warp_sum(heads); uniq = warp_sum(uniq);
-    bad |= __shfl_xor_sync(0xffffffffu, bad, 16); bad |= __shfl_xor_sync(0xffffffffu, bad, 8);
-    bad |= __shfl_xor_sync(0xffffffffu, bad, 4);  bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
-    bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
-    __shared__ u32 s_h, s_u, s_b;
-    if (threadIdx.x == 0) { s_h = 0; s_u = 0; s_b = 0; }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_h) atomicAdd(&sc->n_reads, (unsigned long long)s_h);
-        if (s_u) atomicAdd(&sc->n_uniq, (unsigned long long)s_u);
-        if (s_b) atomicOr(&sc->flags, s_b);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: per-reference segmented reduction over the interleaved bins.  Replaces
-// bins_coverage::none_zero_bin_count (src/reference_contig.hpp:84-91) for cov and uniq_cov and
-// recovers reads_count / uniq_reads_count as the bin sums (each pair adds 1 to exactly one bin).
-// A warp step is 32 x 16 B = 64 bins; segments are padded to 64 bins (padding stays zero).
-// ------------------------------------------------------------------------------------------------
-#define STATS_STEPS_PER_WARP 16
-__global__ void __launch_bounds__(256)
-k_ref_stats(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict__ off /*[G+1] padded, in bins*/,
-            u32 G, u32 *__restrict__ stats)
-{
-    const u32 lane = threadIdx.x & 31;
-    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 chunk = warp; chunk * STATS_STEPS_PER_WARP < n_steps; chunk += n_warps) {
-        const u64 s0 = chunk * STATS_STEPS_PER_WARP;
-        const u64 s1 = min(s0 + (u64)STATS_STEPS_PER_WARP, n_steps);
-        // reference owning bin s0*64: largest g with off[g] <= bin
-        u32 lo = 0, hi = G;
-        const u64 bin0 = s0 * 64;
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (__ldg(off + mid) <= bin0) lo = mid; else hi = mid; }
-        u32 g = lo;
-        u64 g_end = __ldg(off + g + 1);
-        u32 nz = 0, sum = 0, unz = 0, usum = 0;
-        for (u64 s = s0; s < s1; ++s) {
-            if (s * 64 >= g_end) {
-                nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
-                if (lane == 0 && (nz | unz)) {
-                    atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
-                    if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
-                }
-                nz = sum = unz = usum = 0;
-                while (s * 64 >= g_end) { ++g; g_end = __ldg(off + g + 1); }
-            }
-            const uint4 v = __ldg(hist4 + s * 32 + lane);   // {cov0, ucov0, cov1, ucov1}
-            nz += (v.x != 0) + (v.z != 0); sum += v.x + v.z;
-            unz += (v.y != 0) + (v.w != 0); usum += v.y + v.w;
-        }
-        nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
-        if (lane == 0 && (nz | unz)) {
-            atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
-            if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
-        }
-    }
-}
-
-// nonzero uniq_cov2 bins per reference (raw output only): one warp per reference
-__global__ void k_cov2_nz(const u32 *__restrict__ cov2, const u64 *__restrict__ off, const uint4 *__restrict__ meta,
-                          u32 G, u32 *__restrict__ out)
-{
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= G) return;
-    const u64 a = off[warp];
-    const u32 nb = meta[warp].y;
-    u32 nz = 0;
-    for (u32 b = lane; b < nb; b += 32) nz += cov2[a + b] != 0;
-    nz = warp_sum(nz);
-    if (lane == 0) out[warp] = nz;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4: exact-order quantile cut-offs + valid mask.  Replaces coverage_cut_off /
-// uniq_coverage_cut_off (src/slimm.hpp:328-344,672-688), get_quantile_cut_off (src/misc.hpp:197-216)
-// and the reference loop of filter_alignments (src/slimm.hpp:354-378).
-// grid = 2 CTAs (cov, uniq_cov) x 1024 threads.  The f32 folds are sequential in one thread on
-// purpose: the surviving set must be bit-exact and depends on every rounding.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float f32_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }   // x > 0
-__device__ __forceinline__ float f32_down(float x) { return __uint_as_float(__float_as_uint(x) - 1u); } // x > 0
-
-__global__ void __launch_bounds__(1024)
-k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float q, u32 min_reads,
-          float *__restrict__ cp_all /*[2][G]*/, u32 *__restrict__ scratch /*[2][npow2]*/, u32 npow2,
-          u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes, DevScalars *sc)
-{
-    const u32 which = blockIdx.x;             // 0: cov, 1: uniq_cov
-    if (min_reads == 0) {                     // -mr default: 1 + (matches_count-1)/10000 (src/slimm.hpp:458-459)
-        const u32 R = (u32)sc->n_reads;
-        min_reads = R ? 1u + (R - 1u) / 10000u : 0u;
-    }
-    const u32 tid = threadIdx.x;
-    float *cp = cp_all + (size_t)which * G;
-    u32 *v = scratch + (size_t)which * npow2;
-    __shared__ u32 s_scan[1024];
-    __shared__ u32 s_base, s_n;
-    __shared__ float s_cut;
-    __shared__ bool s_last;
-
-    // cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155)
-    for (u32 g = tid; g < G; g += 1024)
-        cp[g] = __fdiv_rn((float)stats[4 * g + 2 * which], (float)meta[g].y);
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    float cut = 0.0f;
-    if (q < 1.0f) {
-        // ordered compaction of cp[g] over references with unique reads (ascending g)
-        for (u32 g0 = 0; g0 < G; g0 += 1024) {
-            const u32 g = g0 + tid;
-            const u32 keep = (g < G && stats[4 * g + 3] > 0) ? 1u : 0u;
-            s_scan[tid] = keep;
-            __syncthreads();
-            for (u32 d = 1; d < 1024; d <<= 1) {
-                u32 t = tid >= d ? s_scan[tid - d] : 0;
-                __syncthreads();
-                s_scan[tid] += t;
-                __syncthreads();
-            }
-            if (keep) v[s_base + s_scan[tid] - 1] = __float_as_uint(cp[g]);
-            __syncthreads();
-            if (tid == 1023) s_base += s_scan[1023];
-            __syncthreads();
-        }
-        const u32 n = s_base;
-        // total = std::accumulate(v, 0.0f): left fold in reference order, one thread
-        if (tid == 0) {
-            float total = 0.0f;
-            for (u32 i = 0; i < n; ++i) total = __fadd_rn(total, __uint_as_float(v[i]));
-            s_cut = total;
-            s_n = n;
-        }
-        // pad to a power of two and sort ascending (values are >= 0: u32 order == f32 order)
-        u32 m = 1;
-        while (m < n) m <<= 1;
-        for (u32 i = n + tid; i < m; i += 1024) v[i] = 0xFFFFFFFFu;
-        __syncthreads();
-        for (u32 k = 2; k <= m; k <<= 1)
-            for (u32 j = k >> 1; j > 0; j >>= 1) {
-                for (u32 t = tid; t < m; t += 1024) {
-                    u32 p = t ^ j;
-                    if (p > t) {
-                        u32 a = v[t], b = v[p];
-                        bool up = (t & k) == 0;
-                        if ((a > b) == up) { v[t] = b; v[p] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-        if (tid == 0) {
-            const float total = s_cut;
-            float c = 0.0f;
-            if (n > 0) {
-                u32 i = n - 1;
-                if (total > 0.0f && q > 0.0f) {      // q <= 0: (sub/total) < q is never true
-                    // (sub/total) < q  <=>  sub < s*, s* = smallest f32 with fl(s*/total) >= q
-                    // (x -> fl(x/total) is monotone), so the loop needs no division
-                    float s = __fmul_rn(q, total);
-                    if (s <= 0.0f) s = __uint_as_float(1u);
-                    while (__fdiv_rn(s, total) >= q && s > __uint_as_float(1u)) s = f32_down(s);
-                    while (__fdiv_rn(s, total) < q) s = f32_up(s);
-                    float sub = 0.0f;
-                    while (sub < s && i > 0) { sub = __fadd_rn(sub, __uint_as_float(v[i])); --i; }
-                }   // total == 0: 0/0 is NaN, NaN < q is false, the reference loop is not entered
-                c = __uint_as_float(v[i]);
-            }
-            s_cut = c;
-        }
-        __syncthreads();
-        cut = s_cut;
-    }
-    if (tid == 0) {
-        if (which == 0) sc->cut = cut; else sc->ucut = cut;
-        __threadfence();
-        s_last = atomicAdd(&sc->done_ctr, 1u) == 1u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // last CTA: valid set + -v counters (src/slimm.hpp:354-378)
-    __threadfence();
-    const float c0 = *(volatile float *)&sc->cut, c1 = *(volatile float *)&sc->ucut;
-    const float *cpa = cp_all, *ucpa = cp_all + G;
-    u32 nv = 0, fc = 0, fu = 0, fm = 0, rc = 0;
-    unsigned long long pairs = 0;
-    for (u32 g0 = 0; g0 < G; g0 += 1024) {
-        const u32 g = g0 + tid;
-        bool ok = false;
-        if (g < G) {
-            const u32 reads = stats[4 * g + 1];
-            if (reads > 0) {
-                ++rc; pairs += reads;
-                const float a = __ldcg(cpa + g), b = __ldcg(ucpa + g);
-                ok = a >= c0 && b >= c1;
-                if (ok) ++nv;
-                else { fu += b < c1; fm += reads < min_reads; fc += a < c0; }
-            }
-            valid_bytes[g] = ok;
-        }
-        const u32 word = __ballot_sync(0xffffffffu, ok);
-        if ((tid & 31) == 0 && g < G) valid_bits[g >> 5] = word;
-    }
-    nv = warp_sum(nv); fc = warp_sum(fc); fu = warp_sum(fu); fm = warp_sum(fm); rc = warp_sum(rc);
-    pairs = warp_sum64(pairs);
-    if ((tid & 31) == 0) {
-        atomicAdd(&sc->n_valid, nv); atomicAdd(&sc->failed_cov, fc); atomicAdd(&sc->failed_ucov, fu);
-        atomicAdd(&sc->failed_minread, fm); atomicAdd(&sc->ref_count, rc);
-        atomicAdd(&sc->n_pairs, pairs);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5+K6: reassignment + LCA.  One thread per record; the first record of a read whose reference
-// survived the filter is the read's leader and walks the run.  Replaces the read loop of
-// filter_alignments (src/slimm.hpp:380-391, read_stat::update src/read_stat.hpp:98-114),
-// slimm::get_lca (src/slimm.hpp:516-531) and phase 1 of get_reads_lca_count (:536-557).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool is_valid(const u32 *__restrict__ vb, u32 g) { return (__ldg(vb + (g >> 5)) >> (g & 31)) & 1u; }
-
-template <class Rec>
-__global__ void __launch_bounds__(256)
-k_assign(Rec rec, u64 n, const uint4 *__restrict__ meta, const uint4 *__restrict__ lin4, const u32 *__restrict__ top_idx,
-         const u32 *__restrict__ vb, u32 G, u32 half_avg, u32 w, u32 *__restrict__ uniq2, u32 *__restrict__ lca_cnt,
-         u32 *__restrict__ child_mark, u32 *__restrict__ fb_mark, u32 *__restrict__ cov2,
-         unsigned char *__restrict__ res_kind, u32 *__restrict__ res_val, DevScalars *sc)
-{
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u32 n_u2 = 0;
-    for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += stride) {   // block-uniform trip count
-        const u64 i = base + threadIdx.x;
-        u32 kind = 0, key = 0;
-        if (i < n) {
-            const u32 g = rec.refid(i);
-            bool leader = g < G && is_valid(vb, g);
-            const u32 r = leader ? rec.read(i) : 0;
-            if (leader) {                  // an earlier surviving record of this read leads instead
-                u64 j = i;
-                while (j > 0 && rec.read(j - 1) == r) {
-                    --j;
-                    u32 h = rec.refid(j);
-                    if (h < G && is_valid(vb, h)) { leader = false; break; }
-                }
-            }
-            if (leader) {
-                const uint4 la = __ldg(lin4 + 2 * (u64)g), lb = __ldg(lin4 + 2 * (u64)g + 1);
-                u32 eq = 0xFFu, gmax = g;
-                bool multi = false;
-                u64 j = i + 1;
-                while (j < n && rec.read(j) == r) {
-                    const u32 h = rec.refid(j);
-                    if (h < G && h != g && is_valid(vb, h)) {
-                        multi = true;
-                        gmax = max(gmax, h);
-                        const uint4 ha = __ldg(lin4 + 2 * (u64)h), hb = __ldg(lin4 + 2 * (u64)h + 1);
-                        u32 m = (ha.x == la.x) | ((ha.y == la.y) << 1) | ((ha.z == la.z) << 2) | ((ha.w == la.w) << 3) |
-                                ((hb.x == lb.x) << 4) | ((hb.y == lb.y) << 5) | ((hb.z == lb.z) << 6) | ((hb.w == lb.w) << 7);
-                        eq &= m;
-                    }
-                    ++j;
-                }
-                const u64 run_end = j;
-                if (!multi) {              // sole survivor: uniq_reads_count2 / uniq_cov2 (:383-390)
-                    kind = 1; key = g; ++n_u2;
-                    if (cov2) {
-                        const uint4 m = __ldg(meta + g);
-                        u32 center = min(rec.upos(i) + half_avg, m.x);
-                        atomicAdd(cov2 + (((u64)m.w << 32) | m.z) + center / w, 1u);
-                    }
-                    if (res_kind) { res_kind[i] = 1; res_val[i] = g; }
-                } else {                   // level-wise LCA over 8-slot lineages, zeros included
-                    kind = 2;
-                    u32 level, owner;
-                    const bool fb = eq == 0;
-                    if (!fb) { level = __ffs(eq) - 1; owner = g; } else { level = 7; owner = gmax; }
-                    key = owner * 8 + level;
-                    const u32 trow = fb ? __ldg(top_idx + gmax) : 0;
-                    for (u64 k = i; k < run_end; ++k) {         // children[lca] U= S (:555)
-                        const u32 h = rec.refid(k);
-                        if (h < G && is_valid(vb, h)) {
-                            u32 *mk = fb ? fb_mark + (u64)trow * G + h : child_mark + (u64)h * 8 + level;
-                            if (*mk == 0) *mk = 1;
-                        }
-                    }
-                    if (res_kind) {
-                        const u32 *lp = reinterpret_cast<const u32 *>(lin4);
-                        res_kind[i] = 2; res_val[i] = __ldg(lp + (u64)owner * 8 + level);
-                    }
-                }
-            }
-        }
-        warp_agg_add(uniq2, key, kind == 1);
-        warp_agg_add(lca_cnt, key, kind == 2);
-    }
-    n_u2 = warp_sum(n_u2);
-    __shared__ u32 s_u2;
-    if (threadIdx.x == 0) s_u2 = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0 && n_u2) atomicAdd(&s_u2, n_u2);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_u2) atomicAdd(&sc->n_uniq2, (unsigned long long)s_u2);
-}
-
-// ------------------------------------------------------------------------------------------------
-// helpers for the unsorted-input path and bin readout
-// ------------------------------------------------------------------------------------------------
-__global__ void k_pack_values(const u32 *__restrict__ ref, const i32 *__restrict__ pos, u64 n, uint2 *__restrict__ out)
-{
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = make_uint2(ref[i], (u32)pos[i]);
-}
-
-__global__ void k_extract_bins(const u32 *__restrict__ src, u64 first, u32 stride_words, u32 word, u32 nb, u32 *__restrict__ out)
-{
-    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) out[b] = src[(first + b) * stride_words + word];
-}
+#include "kernels.cuh"
+#include "profile_host.h"
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -468,6 +37,14 @@ struct slimm_gpu_ctx {
     u32 *d_stats = nullptr; float *d_cp = nullptr; u32 *d_scratch = nullptr;
     u32 *d_valid_bits = nullptr; unsigned char *d_valid_bytes = nullptr;
     u32 *d_assign = nullptr; u64 assign_words = 0;
+    u32 *d_lca_rep = nullptr;               // [LCA_REPLICAS][G*8] spread of the LCA counters
+    // bucketed scatter (histogram larger than L2)
+    u32 *d_items = nullptr; u64 items_cap = 0;
+    u32 *d_bucket_cnt = nullptr, *d_cursor = nullptr;
+    int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
+    bool used_bucket = false;
+    bool finished = false;                  // k_finish_assign ran
+    std::unique_ptr<slimm_host::ProfilePlan> plan;
     DevScalars *d_sc = nullptr;
     u32 *d_tmp_bins = nullptr; u32 tmp_bins_cap = 0;
     // records
@@ -611,6 +188,10 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_valid_bits, ((size_t)G + 31) / 32 * 4 + 4));
     CU(cudaMalloc(&ctx->d_valid_bytes, G));
     CU(cudaMalloc(&ctx->d_assign, ctx->assign_words * 4));
+    CU(cudaMalloc(&ctx->d_lca_rep, (size_t)LCA_REPLICAS * 8 * G * 4));
+    CU(cudaMalloc(&ctx->d_bucket_cnt, MAX_BUCKETS * 4));
+    CU(cudaMalloc(&ctx->d_cursor, MAX_BUCKETS * 4));
+    if (const char *e = getenv("SLIMM_GPU_SCATTER")) ctx->scatter_mode = !strcmp(e, "direct") ? 0 : !strcmp(e, "bucket") ? 1 : -1;
     CU(cudaMalloc(&ctx->d_sc, sizeof(DevScalars)));
     CU(cudaMemcpy(ctx->d_lin, ctx->h_lin.data(), (size_t)G * 32, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_top_idx, ctx->h_top_idx.data(), (size_t)G * 4, cudaMemcpyHostToDevice));
@@ -639,6 +220,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
+    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_bucket_cnt); cudaFree(ctx->d_cursor);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -654,7 +236,7 @@ int slimm_gpu_reset(slimm_gpu_ctx *ctx, uint32_t bin_width, uint32_t avg_read_le
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->external) { ctx->d_rid = ctx->d_ref = nullptr; ctx->d_pos = nullptr; ctx->cap = 0; ctx->external = false; }
-    ctx->n = 0; ctx->stage = ST_CREATED; ctx->use_sorted = false; ctx->have_global_hits = false; ctx->h_assign_ok = false;
+    ctx->n = 0; ctx->stage = ST_CREATED; ctx->use_sorted = false; ctx->have_global_hits = false; ctx->h_assign_ok = false; ctx->finished = false;
     if (avg_read_length) ctx->avg = avg_read_length;
     if (bin_width && bin_width != ctx->w) { ctx->w = bin_width; return layout_bins(ctx); }
     return SLIMM_GPU_OK;
@@ -723,27 +305,71 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
     return SLIMM_GPU_OK;
 }
 
-static int launch_coverage(slimm_gpu_ctx *ctx)
+}  // extern "C" (templates need C++ linkage)
+
+// histogram slices of 2^22 bins (32 MB of interleaved u64) stay L2-resident while a bucket is applied
+#define BUCKET_SHIFT 22
+
+template <class Rec>
+static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
-    const int grid = grid_for(ctx, ctx->n, 256, 8);
     const u32 half = ctx->avg / 2u;
-    if (ctx->use_sorted) {
-        RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
-        k_coverage<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_sc);
-    } else {
-        RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
-        k_coverage<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_sc);
+    const u64 n = ctx->n;
+    if (!ctx->used_bucket) {
+        TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
+        const int grid = grid_for(ctx, (n + COV_ROWS - 1) / COV_ROWS, 256, 8);
+        k_coverage<Rec, 0><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, nullptr, nullptr, 0, 0, ctx->d_sc);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return SLIMM_GPU_OK;
     }
-    ctx->launches++;
+    const u32 n_buckets = (u32)((ctx->Bp + (1ull << BUCKET_SHIFT) - 1) >> BUCKET_SHIFT);
+    if (ctx->items_cap < n) {
+        cudaFree(ctx->d_items); ctx->d_items = nullptr;
+        CU(cudaMalloc(&ctx->d_items, ((n + 3) & ~3ull) * 4));
+        ctx->items_cap = n;
+    }
+    {
+        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);
+        CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, MAX_BUCKETS * 4, ctx->stream));
+        k_bucket_count<Rec><<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, BUCKET_SHIFT, n_buckets,
+                                                                               ctx->d_bucket_cnt, ctx->d_sc);
+        k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, ctx->d_cursor);
+        ctx->launches += 2;
+    }
+    {
+        TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
+        const int grid = grid_for(ctx, (n + COV_ROWS - 1) / COV_ROWS, 256, 6);
+        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_items, ctx->d_cursor,
+                                                         BUCKET_SHIFT, n_buckets, ctx->d_sc);
+        ctx->launches++;
+    }
+    {
+        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
+        const u64 n4 = n >> 2;
+        const u64 blocks = std::max<u64>(1, (n4 + 1023) / 1024);
+        k_accumulate<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_items, n, ctx->d_hist);
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     return SLIMM_GPU_OK;
+}
+
+extern "C" {
+
+static int launch_coverage(slimm_gpu_ctx *ctx)
+{
+    // bucketed scatter when the interleaved histogram is much larger than L2 (and bin ids fit 31 bits)
+    const bool big = ctx->Bp * 8 > (96ull << 20) && ctx->n >= (1u << 20);
+    ctx->used_bucket = ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
+    if (ctx->use_sorted) return launch_coverage_t(ctx, RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted});
+    return launch_coverage_t(ctx, RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos});
 }
 
 static int zero_state(slimm_gpu_ctx *ctx)
 {
     TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
     CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
-    if (ctx->d_cov2) CU(cudaMemsetAsync(ctx->d_cov2, 0, std::max<u64>(ctx->Bp, 64) * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
     return SLIMM_GPU_OK;
 }
@@ -787,11 +413,11 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
     CU(cudaEventRecord(ctx->upload_done, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) ctx->ev_used[i] = false;
-    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false;
+    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false;
     int rc = zero_state(ctx);
     if (rc) return rc;
     if (ctx->n) {
-        { TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE); rc = launch_coverage(ctx); }
+        rc = launch_coverage(ctx);
         if (rc) return rc;
         // optimistic: the kernel assumed non-decreasing read ids and verified it on the fly
         u32 flags = 0;
@@ -802,7 +428,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
             ctx->was_sorted = false;
             rc = sort_records(ctx); if (rc) return rc;
             rc = zero_state(ctx); if (rc) return rc;
-            { TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE); rc = launch_coverage(ctx); }
+            rc = launch_coverage(ctx);
             if (rc) return rc;
         }
     }
@@ -853,6 +479,12 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
         k_cutoffs<<<2, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_scratch,
                                                ctx->npow2, ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
         ctx->launches++;
+        if (ctx->d_cov2 && ctx->Bp) {   // uniq_cov2 starts as uniq_cov of the surviving references
+            const u64 n_steps = ctx->Bp / 64;
+            k_cov2_base<<<grid_for(ctx, n_steps * 32, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, n_steps, ctx->d_off, ctx->G,
+                                                                                     ctx->d_valid_bits, (uint2 *)ctx->d_cov2);
+            ctx->launches++;
+        }
         CU(cudaGetLastError());
     }
     ctx->stage = ST_FILTER;
@@ -873,25 +505,27 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     }
     TimeScope ts(ctx, SLIMM_GPU_T_ASSIGN);
     CU(cudaMemsetAsync(ctx->d_assign, 0, ctx->assign_words * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_lca_rep, 0, (size_t)LCA_REPLICAS * 8 * G * 4, ctx->stream));
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
+    u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     if (ctx->n) {
-        u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
         const int grid = grid_for(ctx, ctx->n, 256, 8);
         const u32 half = ctx->avg / 2u;
         if (ctx->use_sorted) {
             RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
             k_assign<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, (const uint4 *)ctx->d_lin, ctx->d_top_idx, ctx->d_valid_bits,
-                                                    G, half, ctx->w, uniq2, lca, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val, ctx->d_sc);
+                                                    G, half, ctx->w, uniq2, ctx->d_lca_rep, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val);
         } else {
             RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
             k_assign<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, (const uint4 *)ctx->d_lin, ctx->d_top_idx, ctx->d_valid_bits,
-                                                    G, half, ctx->w, uniq2, lca, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val, ctx->d_sc);
+                                                    G, half, ctx->w, uniq2, ctx->d_lca_rep, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val);
         }
-        ctx->launches++;
+        k_fold_lca<<<(8 * G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lca_rep, 8 * G, lca);
+        ctx->launches += 2;
         CU(cudaGetLastError());
     }
     ctx->stage = ST_ASSIGN;
-    ctx->h_assign_ok = false;
+    ctx->h_assign_ok = false; ctx->finished = false;
     return SLIMM_GPU_OK;
 }
 
@@ -899,6 +533,19 @@ int slimm_gpu_assign_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32)
 {
     if (!ctx || !d_ptr || !n_u32) return SLIMM_GPU_EINVAL;
     *d_ptr = ctx->d_assign; *n_u32 = ctx->assign_words;
+    return SLIMM_GPU_OK;
+}
+
+// adds the unique reads of the surviving references to uniq_reads_count2 and totals uniq_matches_count2;
+// lazily, once, after the caller had the chance to sum the per-rank partials
+static int finish_assign(slimm_gpu_ctx *ctx)
+{
+    if (ctx->finished || ctx->stage < ST_ASSIGN) return SLIMM_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    k_finish_assign<<<(ctx->G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_assign, ctx->d_stats, ctx->d_valid_bits, ctx->G, ctx->d_sc);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->finished = true;
     return SLIMM_GPU_OK;
 }
 
@@ -917,6 +564,7 @@ int slimm_gpu_get_summary(slimm_gpu_ctx *ctx, slimm_gpu_summary *out)
     if (!ctx || !out) return SLIMM_GPU_EINVAL;
     if (ctx->stage < ST_COVERAGE) return fail(ctx, SLIMM_GPU_ESTATE, "nothing has run yet");
     CU(cudaSetDevice(ctx->device));
+    { int rc = finish_assign(ctx); if (rc) return rc; }
     DevScalars s;
     CU(cudaMemcpyAsync(&s, ctx->d_sc, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -936,6 +584,7 @@ static int fetch_assign(slimm_gpu_ctx *ctx)
     if (ctx->h_assign_ok) return SLIMM_GPU_OK;
     if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
     CU(cudaSetDevice(ctx->device));
+    { int rc = finish_assign(ctx); if (rc) return rc; }
     ctx->h_assign.resize(ctx->assign_words);
     CU(cudaMemcpyAsync(ctx->h_assign.data(), ctx->d_assign, ctx->assign_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1076,6 +725,52 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
             ++m;
         }
     *n = m;
+    return SLIMM_GPU_OK;
+}
+
+// ---- profile tail fed from the context -----------------------------------------------------------
+int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa_id, const uint8_t *taxa_rank, const uint8_t *taxa_has_name)
+{
+    if (!ctx || (n_taxa && (!taxa_id || !taxa_rank || !taxa_has_name))) return SLIMM_GPU_EINVAL;
+    ctx->plan.reset(new slimm_host::ProfilePlan(ctx->G, ctx->h_len.data(), ctx->h_lin.data(), n_taxa, taxa_id, taxa_rank, taxa_has_name));
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off, slimm_profile_row *rows, uint64_t cap, uint64_t *n)
+{
+    if (!ctx || !n) return SLIMM_GPU_EINVAL;
+    if (!ctx->plan) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_set_taxa has not been called");
+    int rc = fetch_assign(ctx);
+    if (rc) return rc;
+    slimm_gpu_summary sm;
+    rc = slimm_gpu_get_summary(ctx, &sm);
+    if (rc) return rc;
+    const u32 G = ctx->G;
+    const u32 *uniq2 = ctx->h_assign.data(), *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
+    slimm_host::ProfilePlan &pl = *ctx->plan;
+    pl.begin();
+    for (u64 s = 0; s < (u64)G * 8; ++s)
+        if (lca[s]) pl.add_direct(pl.slot_t[s], lca[s]);
+    // children in ascending reference order per taxon keeps the sets sorted without a sort
+    for (u32 g = 0; g < G; ++g) {
+        for (u32 l = 0; l < 8; ++l)
+            if (cm[(u64)g * 8 + l]) pl.add_child(pl.slot_t[(u64)g * 8 + l], g);
+        for (u32 t = 0; t < ctx->n_top; ++t)
+            if (fb[(u64)t * G + g]) { int ti = pl.find(ctx->h_top_vals[t]); if (ti >= 0) pl.add_child((u32)ti, g); }
+    }
+    std::vector<slimm_profile_row> out;
+    rc = pl.finish(uniq2, sm.matches_count, ctx->avg, sm.coverage_cut_off, abundance_cut_off, rank, out);
+    if (rc) return fail(ctx, rc, "profile aggregation failed (inconsistent stage outputs)");
+    *n = out.size();
+    for (u64 i = 0; i < out.size() && i < cap; ++i)
+        if (rows) rows[i] = out[i];
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_set_scatter_mode(slimm_gpu_ctx *ctx, int mode)
+{
+    if (!ctx || mode < -1 || mode > 1) return SLIMM_GPU_EINVAL;
+    ctx->scatter_mode = mode;
     return SLIMM_GPU_OK;
 }
 

@@ -63,21 +63,29 @@ def test_golden_case(case_name, run_name):
     w = run.bin_width or case.avg_read_length
     res = oracle.run(case.ref_len, case.lineage, w, case.avg_read_length, run.cov_cut_off, case.read_id, case.ref_id,
                      case.begin_pos, run.min_reads)
+    taxa = {t: (case.rank_of[t], case.name_of[t]) for t in case.rank_of}
     with api.SlimmGpu(case.ref_len, case.lineage, w, case.avg_read_length,
                       flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
-        # two batches, to cover a read that straddles a push boundary
-        h = case.read_id.size // 2
-        gpu.push(case.read_id[:h], case.ref_id[:h], case.begin_pos[:h])
-        gpu.push(case.read_id[h:], case.ref_id[h:], case.begin_pos[h:])
-        gpu.run(run.cov_cut_off, run.min_reads)
-        compare_with_oracle(gpu, res, case.lineage, check_bins=case.ref_len.size <= 64)
-        s = gpu.summary()
-        taxa = {t: (case.rank_of[t], case.name_of[t]) for t in case.rank_of}
-        rows = api.profile_rows(case.ref_len, case.lineage, taxa, gpu.lca_counts(), gpu.lca_children(),
-                                gpu.ref_stats().uniq_reads_count2, s.matches_count, case.avg_read_length,
-                                s.coverage_cut_off, run.abundance_cut_off, run.rank)
-        lines = report.profile_lines(rows, case.lineage, case.name_of, run.rank)
-        assert_profiles_match(os.path.join(run.path, "profile.tsv"), lines)
+        gpu.set_taxa(taxa)
+        for mode in (0, 1):   # direct REDs, then the bucketed multisplit scatter
+            gpu.reset()
+            gpu.set_scatter_mode(mode)
+            # two batches, to cover a read that straddles a push boundary
+            h = case.read_id.size // 2
+            gpu.push(case.read_id[:h], case.ref_id[:h], case.begin_pos[:h])
+            gpu.push(case.read_id[h:], case.ref_id[h:], case.begin_pos[h:])
+            gpu.run(run.cov_cut_off, run.min_reads)
+            compare_with_oracle(gpu, res, case.lineage, check_bins=case.ref_len.size <= 64)
+            s = gpu.summary()
+            # the host tail fed from the taxon lists ...
+            rows = api.profile_rows(case.ref_len, case.lineage, taxa, gpu.lca_counts(), gpu.lca_children(),
+                                    gpu.ref_stats().uniq_reads_count2, s.matches_count, case.avg_read_length,
+                                    s.coverage_cut_off, run.abundance_cut_off, run.rank)
+            lines = report.profile_lines(rows, case.lineage, case.name_of, run.rank)
+            assert_profiles_match(os.path.join(run.path, "profile.tsv"), lines)
+            # ... and straight from the context
+            rows2 = gpu.profile(run.rank, run.abundance_cut_off)
+            assert report.profile_lines(rows2, case.lineage, case.name_of, run.rank) == lines
 
 
 def _synthetic(G, N, seed, **kw):
@@ -89,6 +97,7 @@ def _synthetic(G, N, seed, **kw):
     return contigs, rec, lineage
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("shuffle", [False, True])
 @pytest.mark.parametrize("G,N,w,cc,kw", [
     (1000, 1_000_000, 1000, 0.95, dict(multi_frac=0.2)),
@@ -97,10 +106,11 @@ def _synthetic(G, N, seed, **kw):
     (3, 50_000, 7, 0.95, dict(multi_frac=0.5, k_lo=2, k_hi=3, neigh=2, len_lo=500, len_hi=3000)),
     (4097, 200_000, 250, 0.9, dict(multi_frac=0.3, len_lo=20_000, len_hi=50_000)),
 ])
-def test_synthetic_vs_oracle(G, N, w, cc, kw, shuffle):
+def test_synthetic_vs_oracle(G, N, w, cc, kw, shuffle, mode):
     contigs, rec, lineage = _synthetic(G, N, 1234 + G, shuffle=shuffle, **kw)
     res = oracle.run(contigs.lengths, lineage, w, 100, cc, rec.read_id, rec.ref_id, rec.begin_pos)
     with api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
+        gpu.set_scatter_mode(mode)
         gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
         gpu.run(cc)
         assert gpu.summary().input_was_sorted == (0 if shuffle else 1)
@@ -126,10 +136,12 @@ def test_edge_cases():
     for name, (rid, ref, pos) in cases.items():
         for cc in (0.95, 1.0, 0.0):
             res = oracle.run(ref_len, lineage, 10, 100, cc, rid, ref, pos)
-            with api.SlimmGpu(ref_len, lineage, 10, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
-                gpu.push(rid, ref, pos)
-                gpu.run(cc)
-                compare_with_oracle(gpu, res, lineage)
+            for mode in (0, 1):
+                with api.SlimmGpu(ref_len, lineage, 10, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
+                    gpu.set_scatter_mode(mode)
+                    gpu.push(rid, ref, pos)
+                    gpu.run(cc)
+                    compare_with_oracle(gpu, res, lineage)
 
 
 def test_bad_reference_id_is_rejected():
@@ -150,3 +162,29 @@ def test_reset_reuses_context():
             gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
             gpu.run(0.95)
             compare_with_oracle(gpu, res, lineage)
+
+
+def test_bucketed_scatter_many_buckets():
+    """Fine bins over long contigs: the padded histogram spans > 20 buckets of 2^22 bins."""
+    contigs, rec, lineage = _synthetic(40, 2_000_000, 77, len_lo=2_000_000, len_hi=6_000_000, multi_frac=0.3)
+    w = 2
+    res = oracle.run(contigs.lengths, lineage, w, 100, 0.95, rec.read_id, rec.ref_id, rec.begin_pos)
+    assert int(res.bin_off[-1]) > 20 * (1 << 22)
+    for mode, flags in ((1, api.KEEP_UNIQ_COV2 | api.READ_RESULTS), (-1, 0)):
+        with api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=flags) as gpu:
+            gpu.set_scatter_mode(mode)
+            gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
+            gpu.run(0.95)
+            if flags:
+                compare_with_oracle(gpu, res, lineage, check_bins=False)
+                for g in (0, 7, 39):
+                    a, b = int(res.bin_off[g]), int(res.bin_off[g + 1])
+                    np.testing.assert_array_equal(gpu.fetch_bins(0, g), res.cov[a:b])
+                    np.testing.assert_array_equal(gpu.fetch_bins(1, g), res.uniq_cov[a:b])
+                    np.testing.assert_array_equal(gpu.fetch_bins(2, g), res.uniq_cov2[a:b])
+            else:
+                st = gpu.ref_stats()
+                np.testing.assert_array_equal(st.reads_count, res.reads_count)
+                np.testing.assert_array_equal(st.uniq_reads_count2, res.uniq_reads_count2)
+                np.testing.assert_array_equal(st.nz_bins, res.nz)
+                assert gpu.lca_counts() == res.direct
