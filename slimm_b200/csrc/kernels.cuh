@@ -11,7 +11,8 @@
 //   ref_meta  : uint4[G] = {len, nb = len/w+1, bin offset lo, hi}; offsets padded to 64 bins so every
 //               512-byte warp step of the stats kernel belongs to one reference
 //   hist      : u64[Bp]  = {lo: cov bin, hi: uniq_cov bin} interleaved: one 64-bit RED per (read, ref) pair
-//   items     : u32[N]   bucketed scatter stream: padded bin index | uniq << 31 (0xFFFFFFFF = repeat hit)
+//   items     : u32[N]   per record, in record order: padded bin index | uniq << 31 (0xFFFFFFFF = repeat hit);
+//               grouped : u32[<=N] the same words grouped by histogram slice (k_split)
 //   cov2      : u32[Bp]  uniq_cov2 (only with SLIMM_GPU_KEEP_UNIQ_COV2)
 //   stats     : u32[G*4] = {nz, reads_count, uniq nz, uniq_reads_count}
 //   assign    : u32[(17+T)*G] = uniq_reads_count2[G] | lca_count[G*8] | child_mark[G*8] | fb_mark[T*G]
@@ -27,7 +28,6 @@ typedef int32_t i32;
 #define FULL 0xffffffffu
 #define ITEM_SKIP 0xFFFFFFFFu
 #define LCA_REPLICAS 16
-#define MAX_BUCKETS 1024
 
 struct DevScalars {
     unsigned long long n_reads;   // matches_count   (partial per rank)      } summed across ranks
@@ -94,121 +94,210 @@ __device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32
 }
 
 // ------------------------------------------------------------------------------------------------
-// Run analysis for one warp-row of 32 consecutive records.  A read is a run of equal read_id.  For
-// its record each lane learns
-//   head  : first record of its read,
-//   first : first record of its (read, ref) pair in file order - only these contribute
-//           (repeat hits are dropped, reference src/read_stat.hpp:125-131),
-//   multi : the read names another reference as well (not unique, src/read_stat.hpp:72-75).
-// Runs inside the row are resolved with two MATCH.ANY; only the runs touching the row's two edges
-// look at neighbouring rows.  bad |= 1 when read ids decrease (input not grouped by read).
+// Sliding 32-record window over the read-grouped record stream.  A read is a run of equal read_id.
+// A window always STARTS at the head of a run; every run that also ends inside the window is
+// "whole" and is resolved with ballots and bit masks alone - no per-thread rescans, no carried
+// state.  The window that follows starts at the head of the first run that did not end here, so a
+// record is analysed exactly once (as a lane of a whole run).  A run longer than 32 records never
+// fits a window: the warp walks it cooperatively (the *_long_run functions).
 // ------------------------------------------------------------------------------------------------
+struct Window {
+    u32 r, g;        // read id / reference id of this lane's record
+    u32 M;           // lanes of my run when it is whole, else 0
+    int s, e;        // first / last lane of my run (valid when whole)
+    bool whole;      // my run starts and ends inside the window and is owned by this chunk
+    bool long_run;   // warp-uniform: the window holds one run only and it does not end here
+    u64 next;        // warp-uniform: head of the first run not resolved here
+};
+
 template <class Rec>
-__device__ __forceinline__ void analyze_row(const Rec &rec, u64 row0, u64 n, bool active, u32 r, u32 g,
-                                            bool &head, bool &first, bool &multi, u32 &bad)
+__device__ __forceinline__ void load_window(const Rec &rec, u64 p, u64 n, u64 chunk_end, u32 lane, Window &w, u32 &bad)
 {
-    const u32 lane = threadIdx.x & 31;
-    const unsigned act = __ballot_sync(FULL, active);
-    const u32 n_act = __popc(act);                      // active lanes are 0..n_act-1
-    u32 edge_lo = 0, edge_hi = 0;                       // read ids just before / after this row
-    bool has_lo = false, has_hi = false;
-    if (lane == 0 && row0 > 0 && row0 < n) { edge_lo = rec.read(row0 - 1); has_lo = true; }
-    if (lane == 0 && row0 + n_act < n) { edge_hi = rec.read(row0 + n_act); has_hi = true; }
-    edge_lo = __shfl_sync(FULL, edge_lo, 0); edge_hi = __shfl_sync(FULL, edge_hi, 0);
-    has_lo = __shfl_sync(FULL, (int)has_lo, 0); has_hi = __shfl_sync(FULL, (int)has_hi, 0);
-    u32 prev = __shfl_up_sync(FULL, r, 1);
-    if (lane == 0) prev = edge_lo;
-    head = first = multi = false;
-    if (!active) return;
-    if ((lane > 0 || has_lo) && prev > r) bad |= 1u;
-    const unsigned M = __match_any_sync(act, r);
-    const unsigned P = __match_any_sync(act, ((unsigned long long)r << 32) | g);
-    head = lane == (u32)(__ffs(M) - 1);
-    first = lane == (u32)(__ffs(P) - 1);
-    multi = P != M;
-    if ((M & 1u) && has_lo && edge_lo == r) {           // my run started in an earlier row
-        head = false;
-        u64 j = row0;
-        while (first && j > 0 && rec.read(j - 1) == r) {
-            --j;
-            if (rec.refid(j) == g) { first = false; break; }
-            multi = true;
-        }
+    const u64 i = p + lane;
+    const bool in = i < n;
+    const bool has_nx = i + 1 < n;
+    w.r = in ? rec.read(i) : 0u;
+    w.g = in ? rec.refid(i) : 0u;
+    u32 nx = __shfl_down_sync(FULL, w.r, 1);
+    if (lane == 31 && has_nx) nx = rec.read(i + 1);
+    const u32 pv = __shfl_up_sync(FULL, w.r, 1);
+    const bool head = in && (lane == 0 || pv != w.r);
+    const bool last = in && (!has_nx || nx != w.r);
+    if (has_nx && nx < w.r) bad |= 1u;                    // read ids must be non-decreasing
+    const u32 H = __ballot_sync(FULL, head), E = __ballot_sync(FULL, last);
+    const u32 n_in = (u32)min((u64)32, n - p);
+    w.s = 31 - __clz(H & (FULL >> (31 - lane)));
+    const u32 Eg = E & (FULL << lane);
+    w.e = Eg ? __ffs(Eg) - 1 : -1;
+    w.whole = in && w.e >= 0 && p + (u32)w.s < chunk_end;  // runs headed at or after chunk_end belong to the next chunk
+    w.M = w.whole ? ((FULL >> (31 - w.e)) & (FULL << w.s)) : 0u;
+    w.long_run = false;
+    if ((E >> (n_in - 1)) & 1u) w.next = p + n_in;
+    else {
+        const u32 s_last = 31 - __clz(H);
+        w.next = p + s_last;
+        w.long_run = s_last == 0;
     }
-    if (first && !multi && (M >> (n_act - 1)) && has_hi && edge_hi == r) {   // my run continues past this row
-        u64 j = row0 + n_act;
-        while (j < n && rec.read(j) == r) {
-            if (rec.refid(j) != g) { multi = true; break; }
-            ++j;
-        }
+}
+
+// first run head at or after c0 (n when there is none); warp-uniform
+template <class Rec>
+__device__ __forceinline__ u64 find_head(const Rec &rec, u64 c0, u64 n, u32 lane)
+{
+    if (c0 == 0) return 0;
+    for (u64 q = c0; q < n; q += 32) {
+        const u64 i = q + lane;
+        const bool h = i < n && rec.read(i) != rec.read(i - 1);
+        const u32 b = __ballot_sync(FULL, h);
+        if (b) return q + (u32)(__ffs(b) - 1);
+    }
+    return n;
+}
+
+#define CHUNK 2048ull        // records per warp work unit
+#define MAX_BUCKETS 512      // padded bin ids fit 31 bits, slices are >= 2^22 bins
+#define LANE_LT(lane) ((1u << (lane)) - 1u)
+
+// contribution of one record: direct RED into the interleaved histogram, or a 32-bit item
+template <int MODE>
+__device__ __forceinline__ void emit(u64 i, u64 b, bool first, bool multi, unsigned long long *__restrict__ hist,
+                                     u32 *__restrict__ items)
+{
+    if (MODE == 0) {
+        if (first) atomicAdd(hist + b, multi ? 1ull : 0x100000001ull);   // cov += 1 [, uniq_cov += 1]
+    } else {
+        __stcs(items + i, first ? ((u32)b | (multi ? 0u : 0x80000000u)) : ITEM_SKIP);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 coverage.  Replaces reference src/slimm.hpp:194-257 + src/read_stat.hpp:116-135.
-//   MODE 0 (direct) : one 64-bit RED per contributing record straight into hist (histogram fits in L2)
-//   MODE 1 (emit)   : every record emits one 32-bit item into its bin-range bucket (block-level
-//                     multisplit through shared memory); k_accumulate applies the buckets one L2-sized
-//                     histogram slice after the other, so the random read-modify-writes never reach HBM
+// K1 coverage.  Replaces reference src/slimm.hpp:194-257 + src/read_stat.hpp:116-135,72-75.
+// Per record: head (first record of its read), first (first record of its (read, ref) pair in file
+// order - repeat hits are dropped, src/read_stat.hpp:125-131), multi (the read names another
+// reference as well).
+//   MODE 0 (direct) : one 64-bit RED per contributing record straight into hist (histogram ~ L2-sized)
+//   MODE 1 (items)  : items[i] = padded bin | uniq << 31 (ITEM_SKIP for a repeat hit), in record order,
+//                     plus the number of items per histogram slice ("bucket"); k_split then groups the
+//                     items by slice and k_accumulate applies them one L2-resident slice after the
+//                     other, so the random read-modify-writes never reach HBM
 // ------------------------------------------------------------------------------------------------
-#define COV_ROWS 8   // rows of 256 records per block tile
+template <class Rec, int MODE>
+__device__ __noinline__ u64 coverage_long_run(const Rec &rec, u64 p, u64 n, u32 lane, const uint4 *__restrict__ meta, u32 G,
+                                              u32 half_avg, u32 w, unsigned long long *__restrict__ hist,
+                                              u32 *__restrict__ items, u32 shift, u32 *s_cnt, u32 &uniq, u32 &bad)
+{
+    const u32 r0 = rec.read(p), gh = rec.refid(p);
+    bool multi = false;
+    u64 end = p;
+    for (u64 q = p;; q += 32) {                                    // pass 1: where the run ends, one reference or several
+        const u64 i = q + lane;
+        const bool in = i < n && rec.read(i) == r0;
+        const u32 inb = __ballot_sync(FULL, in);
+        multi |= __any_sync(FULL, in && rec.refid(i) != gh);
+        if (inb != FULL) { end = q + (inb == 0 ? 0 : 32 - __clz(inb)); break; }
+    }
+    if (end < n && rec.read(end) < r0) bad |= 1u;
+    if (lane == 0) uniq += !multi;
+    for (u64 q = p; q < end; q += 32) {                            // pass 2: first-occurrence test against the run so far
+        const u64 i = q + lane;
+        const bool in = i < end;
+        u32 g = 0;
+        bool first = false, ok = false;
+        u64 b = 0;
+        if (in) {
+            g = rec.refid(i);
+            ok = g < G;
+            first = multi ? true : i == p;
+            if (multi) for (u64 j = p; j < i; ++j) if (rec.refid(j) == g) { first = false; break; }
+            if (!ok) bad |= 2u;
+            else {
+                b = bin_of(meta, g, rec.upos(i), half_avg, w);
+                emit<MODE>(i, b, first, multi, hist, items);
+            }
+        }
+        if (MODE == 1) {                                           // lanes take turns: a long run is rare
+            const u32 todo = __ballot_sync(FULL, in && ok && first);
+            for (u32 t = todo; t; t &= t - 1) {
+                const int l = __ffs(t) - 1;
+                const u32 bk = __shfl_sync(FULL, (u32)(b >> shift), l);
+                if (lane == 0) s_cnt[bk] += 1;
+                __syncwarp();
+            }
+            if (in && !ok) __stcs(items + i, ITEM_SKIP);
+        }
+    }
+    return end;
+}
+
 template <class Rec, int MODE>
 __global__ void __launch_bounds__(256)
 k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, u32 w,
-           unsigned long long *__restrict__ hist, u32 *__restrict__ items, u32 *__restrict__ cursor, u32 shift,
+           unsigned long long *__restrict__ hist, u32 *__restrict__ items, u32 *__restrict__ bucket_cnt, u32 shift,
            u32 n_buckets, DevScalars *sc)
 {
-    __shared__ u32 s_cnt[MODE ? MAX_BUCKETS : 1], s_base[MODE ? MAX_BUCKETS : 1];
+    __shared__ u32 s_cnt_all[MODE ? 8 * MAX_BUCKETS : 1];          // warp-private slice counters: no atomics
     __shared__ u32 s_h, s_u, s_b;
-    const u32 tid = threadIdx.x;
-    if (MODE) for (u32 b = tid; b < n_buckets; b += 256) s_cnt[b] = 0;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    u32 *s_cnt = s_cnt_all + (MODE ? wid * MAX_BUCKETS : 0);
+    if (MODE) for (u32 b = tid; b < 8 * MAX_BUCKETS; b += 256) s_cnt_all[b] = 0;
     if (tid == 0) { s_h = 0; s_u = 0; s_b = 0; }
     __syncthreads();
     u32 heads = 0, uniq = 0, bad = 0;
-    const u64 tile = 256ull * COV_ROWS;
-    for (u64 t0 = (u64)blockIdx.x * tile; t0 < n; t0 += (u64)gridDim.x * tile) {   // block-uniform trip count
-        u32 item[COV_ROWS], rank[COV_ROWS];
-#pragma unroll
-        for (int k = 0; k < COV_ROWS; ++k) {
-            const u64 row0 = t0 + (u64)k * 256 + (tid & ~31u);
-            const u64 i = row0 + (tid & 31);
-            const bool active = i < n;
-            u32 r = 0, g = 0;
-            if (active) { r = rec.read(i); g = rec.refid(i); }
-            bool head, first, multi;
-            analyze_row(rec, row0, n, active, r, g, head, first, multi, bad);
-            item[k] = ITEM_SKIP; rank[k] = 0xFFFFFFFFu;   // rank: bucket << 16 | slot inside this tile's share
-            if (active) {
-                if (g >= G) { bad |= 2u; }
+    const u64 wg = ((u64)blockIdx.x * blockDim.x + tid) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 c0 = wg * CHUNK; c0 < n; c0 += nw * CHUNK) {
+        const u64 c1 = min((u64)(c0 + CHUNK), n);
+        u64 p = find_head(rec, c0, n, lane);
+        while (p < c1) {
+            Window win;
+            load_window(rec, p, n, c1, lane, win, bad);
+            if (win.long_run) {
+                if (lane == 0) ++heads;
+                p = coverage_long_run<Rec, MODE>(rec, p, n, lane, meta, G, half_avg, w, hist, items, shift, s_cnt, uniq, bad);
+                continue;
+            }
+            const u32 g = win.g;
+            const u32 gh = __shfl_sync(FULL, g, win.whole ? win.s : (int)lane);
+            const u32 Wm = __ballot_sync(FULL, win.whole && g != gh);
+            const bool multi = (Wm & win.M) != 0;                  // the read names another reference as well
+            bool first = (int)lane == win.s;
+            if (Wm) {                                              // some run with several references: repeat hits need a look
+                const u32 same = __match_any_sync(FULL, win.whole ? g : ~lane);
+                if (multi) first = (same & win.M & LANE_LT(lane)) == 0;
+            }
+            u64 b = 0;
+            bool ok = false;
+            if (win.whole) {
+                if ((int)lane == win.s) { ++heads; uniq += !multi; }
+                ok = g < G;
+                if (!ok) { bad |= 2u; if (MODE) __stcs(items + p + lane, ITEM_SKIP); }
                 else {
-                    if (head) { ++heads; uniq += !multi; }
-                    const u64 b = bin_of(meta, g, rec.upos(i), half_avg, w);
-                    if (MODE == 0) {
-                        if (first) atomicAdd(hist + b, multi ? 1ull : 0x100000001ull);   // cov += 1 [, uniq_cov += 1]
-                    } else {
-                        const u32 bucket = (u32)(b >> shift);
-                        rank[k] = (bucket << 16) | atomicAdd(&s_cnt[bucket], 1u);       // tile holds < 2^16 records
-                        if (first) item[k] = (u32)b | (multi ? 0u : 0x80000000u);
-                    }
+                    b = bin_of(meta, g, rec.upos(p + lane), half_avg, w);
+                    emit<MODE>(p + lane, b, first, multi, hist, items);
                 }
             }
-        }
-        if (MODE) {
-            __syncthreads();
-            for (u32 b = tid; b < n_buckets; b += 256) {
-                const u32 c = s_cnt[b];
-                if (c) { s_base[b] = atomicAdd(cursor + b, c); s_cnt[b] = 0; }
+            if (MODE == 1) {
+                const bool cnt = win.whole && ok && first;
+                const u32 act = __ballot_sync(FULL, cnt);
+                if (cnt) {
+                    const u32 bk = (u32)(b >> shift);
+                    const u32 peers = __match_any_sync(act, bk);
+                    if ((int)lane == __ffs(peers) - 1) s_cnt[bk] += __popc(peers);
+                }
+                __syncwarp();
             }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < COV_ROWS; ++k)
-                if (rank[k] != 0xFFFFFFFFu) items[s_base[rank[k] >> 16] + (rank[k] & 0xFFFFu)] = item[k];
-            // no barrier needed here: s_base is rewritten only after the next tile's first barrier
+            p = win.next;
         }
     }
     heads = warp_sum(heads); uniq = warp_sum(uniq); bad = warp_or(bad);
-    if ((tid & 31) == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
+    if (lane == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
     __syncthreads();
+    if (MODE)
+        for (u32 b = tid; b < n_buckets; b += 256) {
+            u32 c = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c += s_cnt_all[k * MAX_BUCKETS + b];
+            if (c) atomicAdd(bucket_cnt + b, c);
+        }
     if (tid == 0) {
         if (s_h) atomicAdd(&sc->n_reads, (unsigned long long)s_h);
         if (s_u) atomicAdd(&sc->n_uniq, (unsigned long long)s_u);
@@ -216,50 +305,128 @@ k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, 
     }
 }
 
-// bucket sizes for the multisplit: every record lands in the bucket of its bin
-template <class Rec>
-__global__ void __launch_bounds__(256)
-k_bucket_count(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, u32 w, u32 shift, u32 n_buckets,
-               u32 *__restrict__ bucket_cnt, DevScalars *sc)
+// exclusive scan of the bucket sizes -> write cursors (one block; n_buckets <= MAX_BUCKETS)
+__global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(const u32 *__restrict__ bucket_cnt, u32 n_buckets, u32 *__restrict__ cursor)
 {
-    __shared__ u32 s_cnt[MAX_BUCKETS];
-    for (u32 b = threadIdx.x; b < n_buckets; b += 256) s_cnt[b] = 0;
-    __syncthreads();
-    u32 bad = 0;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u32 g = rec.refid(i);
-        if (g >= G) { bad = 2u; continue; }
-        atomicAdd(&s_cnt[(u32)(bin_of(meta, g, rec.upos(i), half_avg, w) >> shift)], 1u);
-    }
-    __syncthreads();
-    for (u32 b = threadIdx.x; b < n_buckets; b += 256)
-        if (s_cnt[b]) atomicAdd(bucket_cnt + b, s_cnt[b]);
-    if (bad) atomicOr(&sc->flags, bad);
-}
-
-// exclusive scan of the bucket sizes -> write cursors (one block; n_buckets <= 1024)
-__global__ void __launch_bounds__(1024) k_bucket_scan(const u32 *__restrict__ bucket_cnt, u32 n_buckets, u32 *__restrict__ cursor)
-{
-    __shared__ u32 s[1024];
+    __shared__ u32 s[MAX_BUCKETS];
     const u32 tid = threadIdx.x;
     const u32 v = tid < n_buckets ? bucket_cnt[tid] : 0;
     s[tid] = v;
     __syncthreads();
-    for (u32 d = 1; d < 1024; d <<= 1) {
+    for (u32 d = 1; d < MAX_BUCKETS; d <<= 1) {
         const u32 t = tid >= d ? s[tid - d] : 0;
         __syncthreads();
         s[tid] += t;
         __syncthreads();
     }
     if (tid < n_buckets) cursor[tid] = s[tid] - v;
+    if (tid == MAX_BUCKETS - 1) cursor[MAX_BUCKETS] = s[tid];     // number of items (records minus repeat hits)
 }
 
-// apply the bucketed items in stream order: the blocks in flight work on one or two adjacent
+// ------------------------------------------------------------------------------------------------
+// K1b multisplit: groups the items by histogram slice.  A CTA ranks a tile of 256 x SPLIT_ITEMS items
+// with warp-private counters (MATCH.ANY inside the warp, plain shared-memory read-modify-write by the
+// group leader: no shared atomics), orders the tile by slice in shared memory and copies every slice's
+// share to its reserved place in the output, so the global stores are runs of consecutive words.
+// ------------------------------------------------------------------------------------------------
+#define SPLIT_ITEMS 16
+#define SPLIT_TILE (256 * SPLIT_ITEMS)
+__global__ void __launch_bounds__(256)
+k_split(const u32 *__restrict__ items, u64 n, u32 shift, u32 n_buckets, u32 *__restrict__ cursor, u32 *__restrict__ out)
+{
+    __shared__ u32 s_cnt[8 * MAX_BUCKETS];     // per warp: items of each slice, then the warp's offset inside the slice
+    __shared__ u32 s_off[MAX_BUCKETS];         // tile-local start of each slice
+    __shared__ u32 s_delta[MAX_BUCKETS];       // global start - tile-local start (mod 2^32)
+    __shared__ u32 s_item[SPLIT_TILE];
+    __shared__ unsigned short s_bkt[SPLIT_TILE];
+    __shared__ u32 s_warp_tot[8];
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    u32 *my_cnt = s_cnt + wid * MAX_BUCKETS;
+    const u64 n_tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (u32 b = tid; b < 8 * MAX_BUCKETS; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+        const u64 t0 = tile * SPLIT_TILE;
+        u32 item[SPLIT_ITEMS], where[SPLIT_ITEMS];             // where: slice << 16 | slot inside (warp, slice)
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * 256 + tid;
+            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
+        }
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+            const bool active = item[k] != ITEM_SKIP;
+            const u32 act = __ballot_sync(FULL, active);
+            where[k] = 0xFFFFFFFFu;
+            if (active) {
+                const u32 bk = (item[k] & 0x7FFFFFFFu) >> shift;
+                const u32 peers = __match_any_sync(act, bk);
+                const int leader = __ffs(peers) - 1;
+                u32 old = 0;
+                if ((int)lane == leader) { old = my_cnt[bk]; my_cnt[bk] = old + __popc(peers); }
+                old = __shfl_sync(peers, old, leader);
+                where[k] = (bk << 16) | (old + __popc(peers & LANE_LT(lane)));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // per slice: offsets of the 8 warps, tile total; then the exclusive scan over slices
+        u32 tot[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u32 b = tid + h * 256;
+            u32 run = 0;
+            if (b < n_buckets) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const u32 c = s_cnt[k * MAX_BUCKETS + b]; s_cnt[k * MAX_BUCKETS + b] = run; run += c; }
+            }
+            tot[h] = run;
+        }
+        u32 excl[2], base = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                          // block-wide exclusive scan of tot[h] over tid, halves in order
+            u32 x = tot[h];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+            if (lane == 31) s_warp_tot[wid] = x;
+            __syncthreads();
+            u32 wbase = 0, all = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
+            excl[h] = base + wbase + x - tot[h];
+            base += all;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u32 b = tid + h * 256;
+            if (b < n_buckets) {
+                s_off[b] = excl[h];
+                if (tot[h]) s_delta[b] = atomicAdd(cursor + b, tot[h]) - excl[h];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k)
+            if (where[k] != 0xFFFFFFFFu) {
+                const u32 bk = where[k] >> 16;
+                const u32 pos = s_off[bk] + my_cnt[bk] + (where[k] & 0xFFFFu);
+                s_item[pos] = item[k];
+                s_bkt[pos] = (unsigned short)bk;
+            }
+        __syncthreads();
+        const u32 total = base;                                // items of this tile (thread-uniform)
+        for (u32 j = tid; j < total; j += 256) out[j + s_delta[s_bkt[j]]] = s_item[j];
+        __syncthreads();
+    }
+}
+
+// apply the grouped items in stream order: the blocks in flight work on one or two adjacent
 // L2-resident histogram slices
 __global__ void __launch_bounds__(256)
-k_accumulate(const uint4 *__restrict__ items4, u64 n_items, unsigned long long *__restrict__ hist)
+k_accumulate(const uint4 *__restrict__ items4, const u32 *__restrict__ total, unsigned long long *__restrict__ hist)
 {
+    const u64 n_items = __ldg(total);
     const u64 n4 = n_items >> 2;
     const u64 chunk = 256ull * 4;                       // uint4 per block iteration
     const u64 base = (u64)blockIdx.x * chunk;
@@ -268,15 +435,15 @@ k_accumulate(const uint4 *__restrict__ items4, u64 n_items, unsigned long long *
         const u64 j = base + (u64)k * 256 + threadIdx.x;
         if (j < n4) {
             const uint4 v = __ldcs(items4 + j);
-            if (v.x != ITEM_SKIP) atomicAdd(hist + (v.x & 0x7FFFFFFFu), (v.x >> 31) ? 0x100000001ull : 1ull);
-            if (v.y != ITEM_SKIP) atomicAdd(hist + (v.y & 0x7FFFFFFFu), (v.y >> 31) ? 0x100000001ull : 1ull);
-            if (v.z != ITEM_SKIP) atomicAdd(hist + (v.z & 0x7FFFFFFFu), (v.z >> 31) ? 0x100000001ull : 1ull);
-            if (v.w != ITEM_SKIP) atomicAdd(hist + (v.w & 0x7FFFFFFFu), (v.w >> 31) ? 0x100000001ull : 1ull);
+            atomicAdd(hist + (v.x & 0x7FFFFFFFu), (v.x >> 31) ? 0x100000001ull : 1ull);
+            atomicAdd(hist + (v.y & 0x7FFFFFFFu), (v.y >> 31) ? 0x100000001ull : 1ull);
+            atomicAdd(hist + (v.z & 0x7FFFFFFFu), (v.z >> 31) ? 0x100000001ull : 1ull);
+            atomicAdd(hist + (v.w & 0x7FFFFFFFu), (v.w >> 31) ? 0x100000001ull : 1ull);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n_items & 3)) {   // tail
         const u32 v = reinterpret_cast<const u32 *>(items4)[n4 * 4 + threadIdx.x];
-        if (v != ITEM_SKIP) atomicAdd(hist + (v & 0x7FFFFFFFu), (v >> 31) ? 0x100000001ull : 1ull);
+        atomicAdd(hist + (v & 0x7FFFFFFFu), (v >> 31) ? 0x100000001ull : 1ull);
     }
 }
 
@@ -528,14 +695,102 @@ k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5+K6: reassignment + LCA.  The head record of every read with >= 2 records walks its run
-// (single-record reads are unique reads: their contribution to uniq_reads_count2 is
-// valid[g] * uniq_reads_count[g], added by k_finish_assign without touching the records again).
+// K5+K6: reassignment + LCA over the same sliding windows as k_coverage.  Every lane keeps its own
+// record; a read's surviving set S = targets /\ valid is resolved with ballots restricted to the
+// read's lanes:
+//   |S| = 1 -> sole survivor (src/slimm.hpp:383-390); only reads that BECAME unique through the filter
+//              are counted here (a read with one target is already in uniq_reads_count: k_finish_assign
+//              adds valid[g] * uniq_reads_count[g] without touching the records again)
+//   |S| >= 2 -> level-wise LCA over the 8-slot lineages, zeros included (slimm::get_lca, :516-531): the
+//              first level on which all of S agree, else slot 7 of the largest reference id;
+//              count[lca] += 1 and children[lca] U= S (phase 1 of get_reads_lca_count, :536-557),
+//              both keyed by (reference, level) instead of taxon id.
 // Replaces the read loop of filter_alignments (src/slimm.hpp:380-391, read_stat::update
-// src/read_stat.hpp:98-114), slimm::get_lca (src/slimm.hpp:516-531) and phase 1 of
-// get_reads_lca_count (:536-557).
+// src/read_stat.hpp:98-114), slimm::get_lca and phase 1 of get_reads_lca_count.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_valid(const u32 *__restrict__ vb, u32 g) { return (__ldg(vb + (g >> 5)) >> (g & 31)) & 1u; }
+
+// bit l set: the lineages of g and g0 differ on level l
+__device__ __forceinline__ u32 lineage_diff(const uint4 *__restrict__ lin4, u32 g, const uint4 &a0, const uint4 &b0)
+{
+    const uint4 a = __ldg(lin4 + 2 * (u64)g), b = __ldg(lin4 + 2 * (u64)g + 1);
+    return (u32)(a.x != a0.x) | ((u32)(a.y != a0.y) << 1) | ((u32)(a.z != a0.z) << 2) | ((u32)(a.w != a0.w) << 3) |
+           ((u32)(b.x != b0.x) << 4) | ((u32)(b.y != b0.y) << 5) | ((u32)(b.z != b0.z) << 6) | ((u32)(b.w != b0.w) << 7);
+}
+
+struct AssignOut {
+    u32 *uniq2_extra, *lca_cnt, *child_mark, *fb_mark, *cov2;
+    unsigned char *res_kind;
+    u32 *res_val;
+};
+
+__device__ __forceinline__ void mark_child(const AssignOut &o, const u32 *__restrict__ top_idx, u32 G, u32 h, bool fb, u32 level, u32 owner)
+{
+    u32 *mk = fb ? o.fb_mark + (u64)__ldg(top_idx + owner) * G + h : o.child_mark + (u64)h * 8 + level;
+    if (*mk == 0) *mk = 1;
+}
+
+template <class Rec>
+__device__ __noinline__ u64 assign_long_run(const Rec &rec, u64 p, u64 n, u32 lane, const uint4 *__restrict__ meta,
+                                            const uint4 *__restrict__ lin4, const u32 *__restrict__ top_idx,
+                                            const u32 *__restrict__ vb, u32 G, u32 half_avg, u32 w, const AssignOut &o)
+{
+    const u32 r0 = rec.read(p), gh = rec.refid(p);
+    bool have = false, multi = false, was_multi = false;
+    u32 g0 = 0, neq = 0, gmax = 0;
+    u64 lead = p, end = p;
+    uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0;
+    for (u64 q = p;; q += 32) {
+        const u64 i = q + lane;
+        const bool in = i < n && rec.read(i) == r0;
+        const u32 inb = __ballot_sync(FULL, in);
+        const u32 g = in ? rec.refid(i) : 0u;
+        const bool v = in && g < G && is_valid(vb, g);
+        was_multi |= __any_sync(FULL, in && g != gh);
+        const u32 V = __ballot_sync(FULL, v);
+        if (!have && V) {
+            const int f = __ffs(V) - 1;
+            g0 = __shfl_sync(FULL, g, f);
+            lead = q + f;
+            a0 = __ldg(lin4 + 2 * (u64)g0); b0 = __ldg(lin4 + 2 * (u64)g0 + 1);
+            have = true;
+        }
+        if (have) {
+            const bool d = v && g != g0;
+            const u32 mine = d ? lineage_diff(lin4, g, a0, b0) : 0u;
+            multi |= __any_sync(FULL, d);
+            neq |= __reduce_or_sync(FULL, mine);
+            gmax = max(gmax, __reduce_max_sync(FULL, v ? g : 0u));
+        }
+        if (inb != FULL) { end = q + (inb == 0 ? 0 : 32 - __clz(inb)); break; }
+    }
+    if (!have) return end;
+    if (!multi) {                                                  // sole survivor
+        if (lane == 0) {
+            if (was_multi) {
+                atomicAdd(o.uniq2_extra + g0, 1u);
+                if (o.cov2) atomicAdd(o.cov2 + bin_of(meta, g0, rec.upos(lead), half_avg, w), 1u);
+            }
+            if (o.res_kind) { o.res_kind[p] = 1; o.res_val[p] = g0; }
+        }
+        return end;
+    }
+    const u32 eq = ~neq & 0xFFu;
+    const bool fb = eq == 0;                                       // no level agrees: slot 7 of the largest reference id
+    const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1), owner = fb ? gmax : g0;
+    for (u64 q = p; q < end; q += 32) {                            // children[lca] U= S
+        const u64 i = q + lane;
+        if (i < end) {
+            const u32 h = rec.refid(i);
+            if (h < G && is_valid(vb, h)) mark_child(o, top_idx, G, h, fb, level, owner);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(o.lca_cnt + owner * 8 + level, 1u);
+        if (o.res_kind) { o.res_kind[p] = 2; o.res_val[p] = __ldg(reinterpret_cast<const u32 *>(lin4) + (u64)owner * 8 + level); }
+    }
+    return end;
+}
 
 template <class Rec>
 __global__ void __launch_bounds__(256)
@@ -544,78 +799,74 @@ k_assign(Rec rec, u64 n, const uint4 *__restrict__ meta, const uint4 *__restrict
          u32 *__restrict__ child_mark, u32 *__restrict__ fb_mark, u32 *__restrict__ cov2,
          unsigned char *__restrict__ res_kind, u32 *__restrict__ res_val)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u32 *lca_cnt = lca_rep + (u64)(blockIdx.x % LCA_REPLICAS) * 8 * G;
     const u32 lane = threadIdx.x & 31;
-    for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += stride) {   // block-uniform trip count
-        const u64 i = base + threadIdx.x;
-        const bool active = i < n;
-        u32 r = active ? rec.read(i) : 0;
-        u32 prev = __shfl_up_sync(FULL, r, 1);
-        u32 next = __shfl_down_sync(FULL, r, 1);
-        bool is_lca = false;
-        u32 key = 0;
-        if (active) {
-            if (lane == 0) prev = i > 0 ? rec.read(i - 1) : ~r;
-            if (lane == 31 || i + 1 >= n) next = i + 1 < n ? rec.read(i + 1) : ~r;
-            const bool head = i == 0 || prev != r;
-            if (head && next != r) {                   // single-record read
-                if (res_kind) {
-                    const u32 g = rec.refid(i);
-                    if (g < G && is_valid(vb, g)) { res_kind[i] = 1; res_val[i] = g; }
-                }
-            } else if (head) {
-                const u32 ref0 = rec.refid(i);
-                u32 g0 = 0xFFFFFFFFu, gmax = 0, eq = 0xFFu;
-                u64 lead = i;
-                uint4 la = make_uint4(0, 0, 0, 0), lb = la;
-                bool multi = false, was_multi = false;
-                u64 j = i;
-                do {
-                    const u32 h = rec.refid(j);
-                    was_multi |= h != ref0;
-                    if (h < G && is_valid(vb, h)) {
-                        if (g0 == 0xFFFFFFFFu) {
-                            g0 = gmax = h; lead = j;
-                            la = __ldg(lin4 + 2 * (u64)h); lb = __ldg(lin4 + 2 * (u64)h + 1);
-                        } else if (h != g0) {
-                            multi = true;
-                            gmax = max(gmax, h);
-                            const uint4 ha = __ldg(lin4 + 2 * (u64)h), hb = __ldg(lin4 + 2 * (u64)h + 1);
-                            eq &= (ha.x == la.x) | ((ha.y == la.y) << 1) | ((ha.z == la.z) << 2) | ((ha.w == la.w) << 3) |
-                                  ((hb.x == lb.x) << 4) | ((hb.y == lb.y) << 5) | ((hb.z == lb.z) << 6) | ((hb.w == lb.w) << 7);
-                        }
-                    }
-                    ++j;
-                } while (j < n && rec.read(j) == r);
-                const u64 run_end = j;
-                if (g0 != 0xFFFFFFFFu && !multi) {     // sole survivor (:383-390)
-                    if (was_multi) {                   // the read BECAME unique through the filter
-                        atomicAdd(uniq2_extra + g0, 1u);
-                        if (cov2) atomicAdd(cov2 + bin_of(meta, g0, rec.upos(lead), half_avg, w), 1u);
-                    }
-                    if (res_kind) { res_kind[i] = 1; res_val[i] = g0; }
-                } else if (g0 != 0xFFFFFFFFu) {        // level-wise LCA over 8-slot lineages, zeros included
-                    const bool fb = eq == 0;           // no level agrees: slot 7 of the largest reference id
-                    const u32 level = fb ? 7 : __ffs(eq) - 1, owner = fb ? gmax : g0;
-                    is_lca = true;
-                    key = owner * 8 + level;
-                    const u32 trow = fb ? __ldg(top_idx + gmax) : 0;
-                    for (u64 k = lead; k < run_end; ++k) {              // children[lca] U= S (:555)
-                        const u32 h = rec.refid(k);
-                        if (h < G && is_valid(vb, h)) {
-                            u32 *mk = fb ? fb_mark + (u64)trow * G + h : child_mark + (u64)h * 8 + level;
-                            if (*mk == 0) *mk = 1;
-                        }
-                    }
-                    if (res_kind) {
-                        res_kind[i] = 2;
-                        res_val[i] = __ldg(reinterpret_cast<const u32 *>(lin4) + (u64)owner * 8 + level);
-                    }
-                }
+    AssignOut o{uniq2_extra, lca_rep + (u64)(blockIdx.x % LCA_REPLICAS) * 8 * G, child_mark, fb_mark, cov2, res_kind, res_val};
+    const u64 wg = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
+    u32 bad = 0;
+    for (u64 c0 = wg * CHUNK; c0 < n; c0 += nw * CHUNK) {
+        const u64 c1 = min((u64)(c0 + CHUNK), n);
+        u64 p = find_head(rec, c0, n, lane);
+        while (p < c1) {
+            Window win;
+            load_window(rec, p, n, c1, lane, win, bad);
+            if (win.long_run) {
+                p = assign_long_run(rec, p, n, lane, meta, lin4, top_idx, vb, G, half_avg, w, o);
+                continue;
             }
+            const u32 g = win.g;
+            const bool v = win.whole && g < G && is_valid(vb, g);
+            const u32 V = __ballot_sync(FULL, v);
+            const u32 Vm = V & win.M;                              // surviving records of my read
+            const int f = Vm ? __ffs(Vm) - 1 : (int)lane;
+            const u32 g0 = __shfl_sync(FULL, g, f);                // first survivor in file order
+            const u32 Dm = __ballot_sync(FULL, v && g != g0);
+            const u32 gh = __shfl_sync(FULL, g, win.whole ? win.s : (int)lane);
+            const u32 Wm = __ballot_sync(FULL, win.whole && g != gh);
+            const bool run_multi = (Dm & win.M) != 0;              // |S| >= 2
+            const bool is_head = win.whole && (int)lane == win.s;
+            if (is_head && Vm && !run_multi) {                     // sole survivor
+                if (Wm & win.M) {                                  // it named another reference: it BECAME unique through the filter
+                    atomicAdd(o.uniq2_extra + g0, 1u);
+                    if (o.cov2) atomicAdd(o.cov2 + bin_of(meta, g0, rec.upos(p + f), half_avg, w), 1u);
+                }
+                if (o.res_kind) { o.res_kind[p + lane] = 1; o.res_val[p + lane] = g0; }
+            }
+            if (Dm) {                                              // some read of this window needs an LCA
+                const bool need = v && run_multi;
+                u32 mine = 0;
+                if (need && g != g0) {
+                    const uint4 a0 = __ldg(lin4 + 2 * (u64)g0), b0 = __ldg(lin4 + 2 * (u64)g0 + 1);
+                    mine = lineage_diff(lin4, g, a0, b0);
+                }
+                u32 eq = 0;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    const u32 Nl = __ballot_sync(FULL, (mine >> l) & 1u);
+                    if ((Nl & win.M) == 0) eq |= 1u << l;
+                }
+                const bool fb = run_multi && eq == 0;
+                u32 owner = g0;
+                if (__any_sync(FULL, fb)) {                        // largest surviving reference id of the read
+                    u32 gm = v ? g : 0u;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u32 t = __shfl_down_sync(FULL, gm, d);
+                        if (win.whole && (int)lane + d <= win.e) gm = max(gm, t);
+                    }
+                    const u32 top = __shfl_sync(FULL, gm, win.whole ? win.s : (int)lane);
+                    if (fb) owner = top;
+                }
+                const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1);
+                if (need) mark_child(o, top_idx, G, g, fb, level, owner);
+                const bool is_lca = is_head && run_multi;
+                if (is_lca && o.res_kind) {
+                    o.res_kind[p + lane] = 2;
+                    o.res_val[p + lane] = __ldg(reinterpret_cast<const u32 *>(lin4) + (u64)owner * 8 + level);
+                }
+                warp_agg_add(o.lca_cnt, owner * 8 + level, is_lca);
+            }
+            p = win.next;
         }
-        warp_agg_add(lca_cnt, key, is_lca);
     }
 }
 

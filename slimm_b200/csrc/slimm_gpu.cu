@@ -39,7 +39,7 @@ struct slimm_gpu_ctx {
     u32 *d_assign = nullptr; u64 assign_words = 0;
     u32 *d_lca_rep = nullptr;               // [LCA_REPLICAS][G*8] spread of the LCA counters
     // bucketed scatter (histogram larger than L2)
-    u32 *d_items = nullptr; u64 items_cap = 0;
+    u32 *d_items = nullptr, *d_grouped = nullptr; u64 items_cap = 0; u32 bucket_shift = 22;
     u32 *d_bucket_cnt = nullptr, *d_cursor = nullptr;
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
     bool used_bucket = false;
@@ -190,7 +190,7 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_assign, ctx->assign_words * 4));
     CU(cudaMalloc(&ctx->d_lca_rep, (size_t)LCA_REPLICAS * 8 * G * 4));
     CU(cudaMalloc(&ctx->d_bucket_cnt, MAX_BUCKETS * 4));
-    CU(cudaMalloc(&ctx->d_cursor, MAX_BUCKETS * 4));
+    CU(cudaMalloc(&ctx->d_cursor, (MAX_BUCKETS + 1) * 4));
     if (const char *e = getenv("SLIMM_GPU_SCATTER")) ctx->scatter_mode = !strcmp(e, "direct") ? 0 : !strcmp(e, "bucket") ? 1 : -1;
     CU(cudaMalloc(&ctx->d_sc, sizeof(DevScalars)));
     CU(cudaMemcpy(ctx->d_lin, ctx->h_lin.data(), (size_t)G * 32, cudaMemcpyHostToDevice));
@@ -220,7 +220,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
-    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_bucket_cnt); cudaFree(ctx->d_cursor);
+    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_bucket_cnt); cudaFree(ctx->d_cursor);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -307,7 +307,7 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
 
 }  // extern "C" (templates need C++ linkage)
 
-// histogram slices of 2^22 bins (32 MB of interleaved u64) stay L2-resident while a bucket is applied
+// histogram slices of 2^22 bins (32 MB of interleaved u64) stay L2-resident while their items are applied
 #define BUCKET_SHIFT 22
 
 template <class Rec>
@@ -315,40 +315,43 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
     const u32 half = ctx->avg / 2u;
     const u64 n = ctx->n;
+    const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 6));
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        const int grid = grid_for(ctx, (n + COV_ROWS - 1) / COV_ROWS, 256, 8);
         k_coverage<Rec, 0><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, nullptr, nullptr, 0, 0, ctx->d_sc);
         ctx->launches++;
         CU(cudaGetLastError());
         return SLIMM_GPU_OK;
     }
-    const u32 n_buckets = (u32)((ctx->Bp + (1ull << BUCKET_SHIFT) - 1) >> BUCKET_SHIFT);
+    const u32 shift = ctx->bucket_shift;
+    const u32 n_buckets = (u32)((ctx->Bp + (1ull << shift) - 1) >> shift);
     if (ctx->items_cap < n) {
-        cudaFree(ctx->d_items); ctx->d_items = nullptr;
+        cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); ctx->d_items = nullptr; ctx->d_grouped = nullptr;
         CU(cudaMalloc(&ctx->d_items, ((n + 3) & ~3ull) * 4));
+        CU(cudaMalloc(&ctx->d_grouped, ((n + 3) & ~3ull) * 4));
         ctx->items_cap = n;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);
+        TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
         CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, MAX_BUCKETS * 4, ctx->stream));
-        k_bucket_count<Rec><<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, BUCKET_SHIFT, n_buckets,
-                                                                               ctx->d_bucket_cnt, ctx->d_sc);
-        k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, ctx->d_cursor);
-        ctx->launches += 2;
+        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_items, ctx->d_bucket_cnt,
+                                                         shift, n_buckets, ctx->d_sc);
+        ctx->launches++;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        const int grid = grid_for(ctx, (n + COV_ROWS - 1) / COV_ROWS, 256, 6);
-        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_items, ctx->d_cursor,
-                                                         BUCKET_SHIFT, n_buckets, ctx->d_sc);
-        ctx->launches++;
+        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);   // the multisplit: slice starts, then group the items by slice
+        k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, ctx->d_cursor);
+        const u64 n_tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
+        const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
+        k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_cursor, ctx->d_grouped);
+        ctx->launches += 2;
     }
     {
         TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
         const u64 n4 = n >> 2;
         const u64 blocks = std::max<u64>(1, (n4 + 1023) / 1024);
-        k_accumulate<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_items, n, ctx->d_hist);
+        k_accumulate<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_grouped, ctx->d_cursor + MAX_BUCKETS, ctx->d_hist);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -361,6 +364,8 @@ static int launch_coverage(slimm_gpu_ctx *ctx)
 {
     // bucketed scatter when the interleaved histogram is much larger than L2 (and bin ids fit 31 bits)
     const bool big = ctx->Bp * 8 > (96ull << 20) && ctx->n >= (1u << 20);
+    ctx->bucket_shift = BUCKET_SHIFT;
+    while (((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift) > MAX_BUCKETS) ++ctx->bucket_shift;
     ctx->used_bucket = ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
     if (ctx->use_sorted) return launch_coverage_t(ctx, RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted});
     return launch_coverage_t(ctx, RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos});
@@ -509,7 +514,8 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
     u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     if (ctx->n) {
-        const int grid = grid_for(ctx, ctx->n, 256, 8);
+        const u64 n_chunks = (ctx->n + CHUNK - 1) / CHUNK;
+        const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 8));
         const u32 half = ctx->avg / 2u;
         if (ctx->use_sorted) {
             RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
