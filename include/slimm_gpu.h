@@ -35,7 +35,7 @@ enum {
     SLIMM_GPU_ECUDA = 3,      /* a CUDA runtime call failed, see slimm_gpu_last_error           */
     SLIMM_GPU_ENOMEM = 4,     /* device or pinned-host allocation failed                        */
     SLIMM_GPU_ESTATE = 5,     /* stages called out of order                                     */
-    SLIMM_GPU_ERANGE = 6      /* more than 2^32-1 records (hits_count is u32 in the reference)  */
+    SLIMM_GPU_ERANGE = 6      /* more than 2^32-256 records (hits_count is u32 in the reference) */
 };
 
 /* flags for slimm_gpu_config.flags */
@@ -160,9 +160,10 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_BCOUNT, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_ACCUM,
-       SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF, SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_COUNT };
+       SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF, SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_TAIL_HOST, SLIMM_GPU_T_COUNT };
 int slimm_gpu_enable_timing(slimm_gpu_ctx *ctx, int on);
-/* CUDA-event durations (ms) of the last run, per kernel group, and launches issued since create */
+/* CUDA-event durations (ms) of the last run, per kernel group (SLIMM_GPU_T_TAIL_HOST: host wall time of the rank
+ * aggregation in slimm_gpu_profile, after the results arrived), and launches issued since create */
 int slimm_gpu_get_timings(slimm_gpu_ctx *ctx, float *ms, int n);
 int slimm_gpu_get_launch_count(slimm_gpu_ctx *ctx, uint64_t *n);
 

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libslimm_gpu.so")
 
 KEEP_UNIQ_COV2 = 1
 READ_RESULTS = 2
-TIMING_NAMES = ["sort", "zero", "bucket_count", "coverage", "accumulate", "stats", "cutoff", "assign"]
+TIMING_NAMES = ["sort", "zero", "bucket_count", "coverage", "accumulate", "stats", "cutoff", "assign", "tail_host"]
 
 EXPORTED_SYMBOLS = [
     "slimm_gpu_strerror", "slimm_gpu_last_error", "slimm_gpu_device_count", "slimm_gpu_create", "slimm_gpu_destroy",

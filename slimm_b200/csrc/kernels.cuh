@@ -19,6 +19,7 @@
 //               keyed by (reference, lineage level) instead of taxon id, so no device hash map
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 typedef uint32_t u32;
@@ -44,15 +45,15 @@ struct DevScalars {
 // record accessors: plain SoA, or {read_id[], packed (ref | pos<<32)[]} after the device sort
 struct RecSoA {
     const u32 *rid; const u32 *ref; const i32 *pos;
-    __device__ __forceinline__ u32 read(u64 i) const { return __ldg(rid + i); }
-    __device__ __forceinline__ u32 refid(u64 i) const { return __ldg(ref + i); }
-    __device__ __forceinline__ u32 upos(u64 i) const { return (u32)__ldg(pos + i); }
+    __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
+    __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(ref + i); }
+    __device__ __forceinline__ u32 upos(u32 i) const { return (u32)__ldg(pos + i); }
 };
 struct RecPacked {
     const u32 *rid; const uint2 *rp;
-    __device__ __forceinline__ u32 read(u64 i) const { return __ldg(rid + i); }
-    __device__ __forceinline__ u32 refid(u64 i) const { return __ldg(&rp[i].x); }
-    __device__ __forceinline__ u32 upos(u64 i) const { return __ldg(&rp[i].y); }
+    __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
+    __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(&rp[i].x); }
+    __device__ __forceinline__ u32 upos(u32 i) const { return __ldg(&rp[i].y); }
 };
 
 __device__ __forceinline__ u32 warp_sum(u32 v)
@@ -86,11 +87,19 @@ __device__ __forceinline__ void warp_agg_add(u32 *base, u32 key, bool active)
 
 // padded global bin index of a record (reference src/slimm.hpp:200-201): u32 wrap of beginPos + avg/2,
 // clamp to the contig length, integer division by the bin width
-__device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32 upos, u32 half_avg, u32 w)
+// exact n / d for a divisor fixed per sample: t = umulhi(mul, n); q = (t + ((n - t) >> s1)) >> s2
+// (round-up method; the host derives {mul, s1, s2} from the bin width, slimm_gpu.cu bin_div_for)
+struct BinDiv { u32 mul, s1, s2; };
+__device__ __forceinline__ u32 fast_div(u32 n, const BinDiv &d)
+{
+    const u32 t = __umulhi(d.mul, n);
+    return (t + ((n - t) >> d.s1)) >> d.s2;
+}
+__device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32 upos, u32 half_avg, const BinDiv &wdiv)
 {
     const uint4 m = __ldg(meta + g);   // {len, nb, off_lo, off_hi}
     const u32 center = min(upos + half_avg, m.x);
-    return (((u64)m.w << 32) | m.z) + center / w;
+    return (((u64)m.w << 32) | m.z) + fast_div(center, wdiv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -100,6 +109,7 @@ __device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32
 // state.  The window that follows starts at the head of the first run that did not end here, so a
 // record is analysed exactly once (as a lane of a whole run).  A run longer than 32 records never
 // fits a window: the warp walks it cooperatively (the *_long_run functions).
+// Record indices are 32-bit: a context holds at most SLIMM_MAX_RECORDS = 2^32 - 256 records.
 // ------------------------------------------------------------------------------------------------
 struct Window {
     u32 r, g;        // read id / reference id of this lane's record
@@ -107,13 +117,34 @@ struct Window {
     int s, e;        // first / last lane of my run (valid when whole)
     bool whole;      // my run starts and ends inside the window and is owned by this chunk
     bool long_run;   // warp-uniform: the window holds one run only and it does not end here
-    u64 next;        // warp-uniform: head of the first run not resolved here
+    u32 next;        // warp-uniform: head of the first run not resolved here
 };
 
-template <class Rec>
-__device__ __forceinline__ void load_window(const Rec &rec, u64 p, u64 n, u64 chunk_end, u32 lane, Window &w, u32 &bad)
+#define LANE_LT(lane) ((1u << (lane)) - 1u)
+#define LANE_LE(lane) (FULL >> (31 - (lane)))
+#define LANE_GE(lane) (FULL << (lane))
+
+// masks from the ballots of run heads (H, bit 0 set) and run ends (E) of a window of n_in records
+__device__ __forceinline__ void window_masks(u32 H, u32 E, u32 n_in, u32 p, u32 chunk_end, u32 lane, bool in, Window &w)
 {
-    const u64 i = p + lane;
+    w.s = 31 - __clz(H & LANE_LE(lane));
+    const u32 Eg = E & LANE_GE(lane);
+    w.e = __ffs(Eg) - 1;
+    w.whole = in && Eg != 0 && p + (u32)w.s < chunk_end;   // runs headed at or after chunk_end belong to the next chunk
+    w.M = w.whole ? (LANE_LE(w.e) & LANE_GE(w.s)) : 0u;
+    w.long_run = false;
+    if ((E >> (n_in - 1)) & 1u) w.next = p + n_in;
+    else {
+        const u32 s_last = 31 - __clz(H);
+        w.next = p + s_last;
+        w.long_run = s_last == 0;
+    }
+}
+
+template <class Rec>
+__device__ __forceinline__ void load_window(const Rec &rec, u32 p, u32 n, u32 chunk_end, u32 lane, Window &w, u32 &bad)
+{
+    const u32 i = p + lane;
     const bool in = i < n;
     const bool has_nx = i + 1 < n;
     w.r = in ? rec.read(i) : 0u;
@@ -125,28 +156,16 @@ __device__ __forceinline__ void load_window(const Rec &rec, u64 p, u64 n, u64 ch
     const bool last = in && (!has_nx || nx != w.r);
     if (has_nx && nx < w.r) bad |= 1u;                    // read ids must be non-decreasing
     const u32 H = __ballot_sync(FULL, head), E = __ballot_sync(FULL, last);
-    const u32 n_in = (u32)min((u64)32, n - p);
-    w.s = 31 - __clz(H & (FULL >> (31 - lane)));
-    const u32 Eg = E & (FULL << lane);
-    w.e = Eg ? __ffs(Eg) - 1 : -1;
-    w.whole = in && w.e >= 0 && p + (u32)w.s < chunk_end;  // runs headed at or after chunk_end belong to the next chunk
-    w.M = w.whole ? ((FULL >> (31 - w.e)) & (FULL << w.s)) : 0u;
-    w.long_run = false;
-    if ((E >> (n_in - 1)) & 1u) w.next = p + n_in;
-    else {
-        const u32 s_last = 31 - __clz(H);
-        w.next = p + s_last;
-        w.long_run = s_last == 0;
-    }
+    window_masks(H, E, min(32u, n - p), p, chunk_end, lane, in, w);
 }
 
 // first run head at or after c0 (n when there is none); warp-uniform
 template <class Rec>
-__device__ __forceinline__ u64 find_head(const Rec &rec, u64 c0, u64 n, u32 lane)
+__device__ __forceinline__ u32 find_head(const Rec &rec, u32 c0, u32 n, u32 lane)
 {
     if (c0 == 0) return 0;
-    for (u64 q = c0; q < n; q += 32) {
-        const u64 i = q + lane;
+    for (u32 q = c0; q < n; q += 32) {
+        const u32 i = q + lane;
         const bool h = i < n && rec.read(i) != rec.read(i - 1);
         const u32 b = __ballot_sync(FULL, h);
         if (b) return q + (u32)(__ffs(b) - 1);
@@ -154,19 +173,29 @@ __device__ __forceinline__ u64 find_head(const Rec &rec, u64 c0, u64 n, u32 lane
     return n;
 }
 
-#define CHUNK 2048ull        // records per warp work unit
+#define CHUNK 2048u          // records per warp work unit
+#define CW_SLOT (CHUNK + 32) // compact words a chunk can emit (its last run may reach 31 records past the chunk)
+#define LR_SLOT 64u          // long runs a chunk can own (each is longer than 32 records)
+#define CW_HEAD 0x80000000u
 #define MAX_BUCKETS 512      // padded bin ids fit 31 bits, slices are >= 2^22 bins
-#define LANE_LT(lane) ((1u << (lane)) - 1u)
+
+struct CovParams {
+    const uint4 *meta; u32 G, half_avg; BinDiv wdiv;
+    unsigned long long *hist;       // MODE 0
+    u32 *items, *bucket_cnt; u32 shift, n_buckets;   // MODE 1
+    u32 *cw, *cw_idx; uint2 *chunk_cnt; u32 *lr;     // compact stream of the multi-mapped reads for k_assign
+    unsigned char *res_kind;        // optional per-read results: marks the head of every single-target read
+    DevScalars *sc;
+};
 
 // contribution of one record: direct RED into the interleaved histogram, or a 32-bit item
 template <int MODE>
-__device__ __forceinline__ void emit(u64 i, u64 b, bool first, bool multi, unsigned long long *__restrict__ hist,
-                                     u32 *__restrict__ items)
+__device__ __forceinline__ void emit(const CovParams &P, u32 i, u64 b, bool first, bool multi)
 {
     if (MODE == 0) {
-        if (first) atomicAdd(hist + b, multi ? 1ull : 0x100000001ull);   // cov += 1 [, uniq_cov += 1]
+        if (first) atomicAdd(P.hist + b, multi ? 1ull : 0x100000001ull);   // cov += 1 [, uniq_cov += 1]
     } else {
-        __stcs(items + i, first ? ((u32)b | (multi ? 0u : 0x80000000u)) : ITEM_SKIP);
+        __stcs(P.items + i, first ? ((u32)b | (multi ? 0u : 0x80000000u)) : ITEM_SKIP);
     }
 }
 
@@ -178,52 +207,59 @@ __device__ __forceinline__ void emit(u64 i, u64 b, bool first, bool multi, unsig
 //   MODE 0 (direct) : one 64-bit RED per contributing record straight into hist (histogram ~ L2-sized)
 //   MODE 1 (items)  : items[i] = padded bin | uniq << 31 (ITEM_SKIP for a repeat hit), in record order,
 //                     plus the number of items per histogram slice ("bucket"); k_split then groups the
-//                     items by slice and k_accumulate applies them one L2-resident slice after the
+//                     items by slice and k_accumulate_fused applies them one L2-resident slice after the
 //                     other, so the random read-modify-writes never reach HBM
+// Both modes also write the COMPACT STREAM k_assign works on: for every read with several targets its
+// distinct reference ids in file order (bit 31 marks the first), chunk by chunk; the reads with one target
+// (the majority) never come back.  Runs longer than 32 records are listed by their start instead.
 // ------------------------------------------------------------------------------------------------
 template <class Rec, int MODE>
-__device__ __noinline__ u64 coverage_long_run(const Rec &rec, u64 p, u64 n, u32 lane, const uint4 *__restrict__ meta, u32 G,
-                                              u32 half_avg, u32 w, unsigned long long *__restrict__ hist,
-                                              u32 *__restrict__ items, u32 shift, u32 *s_cnt, u32 &uniq, u32 &bad)
+__device__ __noinline__ u32 coverage_long_run(const Rec &rec, u32 p, u32 n, u32 lane, const CovParams &P, u32 *s_cnt, u32 &uniq,
+                                              u32 &bad, u32 lr_base, u32 &n_lr)
 {
     const u32 r0 = rec.read(p), gh = rec.refid(p);
     bool multi = false;
-    u64 end = p;
-    for (u64 q = p;; q += 32) {                                    // pass 1: where the run ends, one reference or several
-        const u64 i = q + lane;
+    u32 end = p;
+    for (u32 q = p;; q += 32) {                                    // pass 1: where the run ends, one reference or several
+        const u32 i = q + lane;
         const bool in = i < n && rec.read(i) == r0;
         const u32 inb = __ballot_sync(FULL, in);
         multi |= __any_sync(FULL, in && rec.refid(i) != gh);
         if (inb != FULL) { end = q + (inb == 0 ? 0 : 32 - __clz(inb)); break; }
     }
     if (end < n && rec.read(end) < r0) bad |= 1u;
-    if (lane == 0) uniq += !multi;
-    for (u64 q = p; q < end; q += 32) {                            // pass 2: first-occurrence test against the run so far
-        const u64 i = q + lane;
+    if (lane == 0) {
+        uniq += !multi;
+        if (multi) { if (n_lr < LR_SLOT) P.lr[lr_base + n_lr] = p; ++n_lr; }
+        else if (P.res_kind) P.res_kind[p] = 3;
+    }
+    n_lr = __shfl_sync(FULL, n_lr, 0);
+    for (u32 q = p; q < end; q += 32) {                            // pass 2: first-occurrence test against the run so far
+        const u32 i = q + lane;
         const bool in = i < end;
         u32 g = 0;
         bool first = false, ok = false;
         u64 b = 0;
         if (in) {
             g = rec.refid(i);
-            ok = g < G;
+            ok = g < P.G;
             first = multi ? true : i == p;
-            if (multi) for (u64 j = p; j < i; ++j) if (rec.refid(j) == g) { first = false; break; }
+            if (multi) for (u32 j = p; j < i; ++j) if (rec.refid(j) == g) { first = false; break; }
             if (!ok) bad |= 2u;
             else {
-                b = bin_of(meta, g, rec.upos(i), half_avg, w);
-                emit<MODE>(i, b, first, multi, hist, items);
+                b = bin_of(P.meta, g, rec.upos(i), P.half_avg, P.wdiv);
+                emit<MODE>(P, i, b, first, multi);
             }
         }
         if (MODE == 1) {                                           // lanes take turns: a long run is rare
             const u32 todo = __ballot_sync(FULL, in && ok && first);
             for (u32 t = todo; t; t &= t - 1) {
                 const int l = __ffs(t) - 1;
-                const u32 bk = __shfl_sync(FULL, (u32)(b >> shift), l);
+                const u32 bk = __shfl_sync(FULL, (u32)(b >> P.shift), l);
                 if (lane == 0) s_cnt[bk] += 1;
                 __syncwarp();
             }
-            if (in && !ok) __stcs(items + i, ITEM_SKIP);
+            if (in && !ok) __stcs(P.items + i, ITEM_SKIP);
         }
     }
     return end;
@@ -231,9 +267,7 @@ __device__ __noinline__ u64 coverage_long_run(const Rec &rec, u64 p, u64 n, u32 
 
 template <class Rec, int MODE>
 __global__ void __launch_bounds__(256)
-k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, u32 w,
-           unsigned long long *__restrict__ hist, u32 *__restrict__ items, u32 *__restrict__ bucket_cnt, u32 shift,
-           u32 n_buckets, DevScalars *sc)
+k_coverage(Rec rec, u32 n, CovParams P)
 {
     __shared__ u32 s_cnt_all[MODE ? 8 * MAX_BUCKETS : 1];          // warp-private slice counters: no atomics
     __shared__ u32 s_h, s_u, s_b;
@@ -243,43 +277,57 @@ k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, 
     if (tid == 0) { s_h = 0; s_u = 0; s_b = 0; }
     __syncthreads();
     u32 heads = 0, uniq = 0, bad = 0;
-    const u64 wg = ((u64)blockIdx.x * blockDim.x + tid) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 c0 = wg * CHUNK; c0 < n; c0 += nw * CHUNK) {
-        const u64 c1 = min((u64)(c0 + CHUNK), n);
-        u64 p = find_head(rec, c0, n, lane);
+    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 wg = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (u32 c = wg; c < n_chunks; c += nw) {
+        const u32 c0 = c * CHUNK, c1 = min(c0 + CHUNK, n);
+        u32 p = find_head(rec, c0, n, lane);
+        u32 n_cw = 0, n_lr = 0;                                    // compact words / long runs of this chunk (warp-uniform)
+        const u64 cw_base = (u64)c * CW_SLOT;
         while (p < c1) {
             Window win;
             load_window(rec, p, n, c1, lane, win, bad);
             if (win.long_run) {
                 if (lane == 0) ++heads;
-                p = coverage_long_run<Rec, MODE>(rec, p, n, lane, meta, G, half_avg, w, hist, items, shift, s_cnt, uniq, bad);
+                p = coverage_long_run<Rec, MODE>(rec, p, n, lane, P, s_cnt, uniq, bad, c * LR_SLOT, n_lr);
                 continue;
             }
             const u32 g = win.g;
             const u32 gh = __shfl_sync(FULL, g, win.whole ? win.s : (int)lane);
             const u32 Wm = __ballot_sync(FULL, win.whole && g != gh);
             const bool multi = (Wm & win.M) != 0;                  // the read names another reference as well
-            bool first = (int)lane == win.s;
-            if (Wm) {                                              // some run with several references: repeat hits need a look
+            const bool is_head = win.whole && (int)lane == win.s;
+            bool first = is_head;
+            if (Wm) {                                              // some read with several references: repeat hits need a look
                 const u32 same = __match_any_sync(FULL, win.whole ? g : ~lane);
                 if (multi) first = (same & win.M & LANE_LT(lane)) == 0;
+                const u32 C = __ballot_sync(FULL, multi && first); // the compact stream keeps the distinct references
+                if (multi && first) {
+                    const u64 at = cw_base + n_cw + __popc(C & LANE_LT(lane));
+                    P.cw[at] = g | (is_head ? CW_HEAD : 0u);
+                    if (P.cw_idx) P.cw_idx[at] = p + lane;
+                }
+                n_cw += __popc(C);
             }
             u64 b = 0;
             bool ok = false;
             if (win.whole) {
-                if ((int)lane == win.s) { ++heads; uniq += !multi; }
-                ok = g < G;
-                if (!ok) { bad |= 2u; if (MODE) __stcs(items + p + lane, ITEM_SKIP); }
+                if (is_head) {
+                    ++heads; uniq += !multi;
+                    if (P.res_kind && !multi) P.res_kind[p + lane] = 3;
+                }
+                ok = g < P.G;
+                if (!ok) { bad |= 2u; if (MODE) __stcs(P.items + p + lane, ITEM_SKIP); }
                 else {
-                    b = bin_of(meta, g, rec.upos(p + lane), half_avg, w);
-                    emit<MODE>(p + lane, b, first, multi, hist, items);
+                    b = bin_of(P.meta, g, rec.upos(p + lane), P.half_avg, P.wdiv);
+                    emit<MODE>(P, p + lane, b, first, multi);
                 }
             }
             if (MODE == 1) {
                 const bool cnt = win.whole && ok && first;
                 const u32 act = __ballot_sync(FULL, cnt);
                 if (cnt) {
-                    const u32 bk = (u32)(b >> shift);
+                    const u32 bk = (u32)(b >> P.shift);
                     const u32 peers = __match_any_sync(act, bk);
                     if ((int)lane == __ffs(peers) - 1) s_cnt[bk] += __popc(peers);
                 }
@@ -287,40 +335,75 @@ k_coverage(Rec rec, u64 n, const uint4 *__restrict__ meta, u32 G, u32 half_avg, 
             }
             p = win.next;
         }
+        if (lane == 0) P.chunk_cnt[c] = make_uint2(n_cw, n_lr);
     }
     heads = warp_sum(heads); uniq = warp_sum(uniq); bad = warp_or(bad);
     if (lane == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
     __syncthreads();
     if (MODE)
-        for (u32 b = tid; b < n_buckets; b += 256) {
+        for (u32 b = tid; b < P.n_buckets; b += 256) {
             u32 c = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) c += s_cnt_all[k * MAX_BUCKETS + b];
-            if (c) atomicAdd(bucket_cnt + b, c);
+            if (c) atomicAdd(P.bucket_cnt + b, c);
         }
     if (tid == 0) {
-        if (s_h) atomicAdd(&sc->n_reads, (unsigned long long)s_h);
-        if (s_u) atomicAdd(&sc->n_uniq, (unsigned long long)s_u);
-        if (s_b) atomicOr(&sc->flags, s_b);
+        if (s_h) atomicAdd(&P.sc->n_reads, (unsigned long long)s_h);
+        if (s_u) atomicAdd(&P.sc->n_uniq, (unsigned long long)s_u);
+        if (s_b) atomicOr(&P.sc->flags, s_b);
     }
 }
 
-// exclusive scan of the bucket sizes -> write cursors (one block; n_buckets <= MAX_BUCKETS)
-__global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(const u32 *__restrict__ bucket_cnt, u32 n_buckets, u32 *__restrict__ cursor)
+// Schedule of the fused zero + accumulate kernel, built on the device from the slice sizes.  Work units are
+// handed out in this order (tickets): Z(0), then for every slice b: Z(b+1), A(b).  Z(b) zero-fills slice b of
+// the histogram (ZERO_TILE bins per unit), A(b) applies ACC_TILE of the slice's items.  A(b) only waits for
+// Z(b), which was handed out a whole slice earlier.
+#define ZERO_TILE 8192u      // bins per zero unit (64 KB of interleaved u64)
+#define ACC_TILE 4096u       // items per accumulate unit
+struct Sched {
+    u32 next_ticket, total_units, total_items, pad;
+    u32 cursor[MAX_BUCKETS];     // k_split's write cursors (start of every slice's items, advanced by the split)
+    u32 start[MAX_BUCKETS];      // start of every slice's items
+    u32 count[MAX_BUCKETS];      // items per slice (filled by k_coverage)
+    u32 first_z[MAX_BUCKETS];    // ticket of the first unit of Z(b+1)
+    u32 first_a[MAX_BUCKETS];    // ticket of the first unit of A(b)
+    u32 zero_done[MAX_BUCKETS];  // finished units of Z(b)
+};
+
+__device__ __forceinline__ u32 zero_units(u64 Bp, u32 shift, u32 b, u32 n_buckets)
 {
-    __shared__ u32 s[MAX_BUCKETS];
+    if (b >= n_buckets) return 0;
+    const u64 lo = (u64)b << shift, hi = min(Bp, (u64)(b + 1) << shift);
+    return (u32)((hi - lo + ZERO_TILE - 1) / ZERO_TILE);
+}
+
+// exclusive scan of the slice sizes -> item starts / write cursors and the unit schedule (one block)
+__global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_buckets, u64 Bp, u32 shift)
+{
+    __shared__ u32 s[MAX_BUCKETS], s2[MAX_BUCKETS];
     const u32 tid = threadIdx.x;
-    const u32 v = tid < n_buckets ? bucket_cnt[tid] : 0;
-    s[tid] = v;
+    const u32 v = tid < n_buckets ? sd->count[tid] : 0;
+    const u32 units = tid < n_buckets ? zero_units(Bp, shift, tid + 1, n_buckets) + (v + ACC_TILE - 1) / ACC_TILE : 0;
+    s[tid] = v; s2[tid] = units;
     __syncthreads();
     for (u32 d = 1; d < MAX_BUCKETS; d <<= 1) {
-        const u32 t = tid >= d ? s[tid - d] : 0;
+        const u32 t = tid >= d ? s[tid - d] : 0, t2 = tid >= d ? s2[tid - d] : 0;
         __syncthreads();
-        s[tid] += t;
+        s[tid] += t; s2[tid] += t2;
         __syncthreads();
     }
-    if (tid < n_buckets) cursor[tid] = s[tid] - v;
-    if (tid == MAX_BUCKETS - 1) cursor[MAX_BUCKETS] = s[tid];     // number of items (records minus repeat hits)
+    if (tid < n_buckets) {
+        sd->cursor[tid] = sd->start[tid] = s[tid] - v;
+        const u32 z0 = zero_units(Bp, shift, 0, n_buckets);
+        sd->first_z[tid] = z0 + s2[tid] - units;
+        sd->first_a[tid] = z0 + s2[tid] - units + zero_units(Bp, shift, tid + 1, n_buckets);
+        sd->zero_done[tid] = 0;
+    }
+    if (tid == MAX_BUCKETS - 1) {
+        sd->total_items = s[tid];                                 // records minus repeat hits
+        sd->total_units = zero_units(Bp, shift, 0, n_buckets) + s2[tid];
+        sd->next_ticket = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,7 +415,7 @@ __global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(const u32 *__restri
 #define SPLIT_ITEMS 16
 #define SPLIT_TILE (256 * SPLIT_ITEMS)
 __global__ void __launch_bounds__(256)
-k_split(const u32 *__restrict__ items, u64 n, u32 shift, u32 n_buckets, u32 *__restrict__ cursor, u32 *__restrict__ out)
+k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out)
 {
     __shared__ u32 s_cnt[8 * MAX_BUCKETS];     // per warp: items of each slice, then the warp's offset inside the slice
     __shared__ u32 s_off[MAX_BUCKETS];         // tile-local start of each slice
@@ -353,19 +436,24 @@ k_split(const u32 *__restrict__ items, u64 n, u32 shift, u32 n_buckets, u32 *__r
             const u64 i = t0 + (u64)k * 256 + tid;
             item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
         }
+        u32 peers[SPLIT_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {                // the MATCHes are independent: all of them in flight at once
             const bool active = item[k] != ITEM_SKIP;
             const u32 act = __ballot_sync(FULL, active);
+            peers[k] = 0;
+            if (active) peers[k] = __match_any_sync(act, (item[k] & 0x7FFFFFFFu) >> shift);
+        }
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {                // ordered updates of the warp's counters
             where[k] = 0xFFFFFFFFu;
-            if (active) {
+            if (peers[k]) {
                 const u32 bk = (item[k] & 0x7FFFFFFFu) >> shift;
-                const u32 peers = __match_any_sync(act, bk);
-                const int leader = __ffs(peers) - 1;
+                const int leader = __ffs(peers[k]) - 1;
                 u32 old = 0;
-                if ((int)lane == leader) { old = my_cnt[bk]; my_cnt[bk] = old + __popc(peers); }
-                old = __shfl_sync(peers, old, leader);
-                where[k] = (bk << 16) | (old + __popc(peers & LANE_LT(lane)));
+                if ((int)lane == leader) { old = my_cnt[bk]; my_cnt[bk] = old + __popc(peers[k]); }
+                old = __shfl_sync(peers[k], old, leader);
+                where[k] = (bk << 16) | (old + __popc(peers[k] & LANE_LT(lane)));
             }
             __syncwarp();
         }
@@ -402,7 +490,7 @@ k_split(const u32 *__restrict__ items, u64 n, u32 shift, u32 n_buckets, u32 *__r
             const u32 b = tid + h * 256;
             if (b < n_buckets) {
                 s_off[b] = excl[h];
-                if (tot[h]) s_delta[b] = atomicAdd(cursor + b, tot[h]) - excl[h];
+                if (tot[h]) s_delta[b] = atomicAdd(&sd->cursor[b], tot[h]) - excl[h];
             }
         }
         __syncthreads();
@@ -421,28 +509,56 @@ k_split(const u32 *__restrict__ items, u64 n, u32 shift, u32 n_buckets, u32 *__r
     }
 }
 
-// apply the grouped items in stream order: the blocks in flight work on one or two adjacent
-// L2-resident histogram slices
+// ------------------------------------------------------------------------------------------------
+// K2 fused zero-fill + accumulate.  One launch; every CTA draws a ticket and looks its unit up in the
+// schedule.  A slice is zero-filled in L2 (full-sector stores, no HBM read), its items are applied as
+// 64-bit REDs that all hit L2, and the slice leaves for HBM once: the random read-modify-writes never
+// miss.  Tickets are handed out in order, so the Z(b) units an A(b) unit waits for are always running.
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_accumulate(const uint4 *__restrict__ items4, const u32 *__restrict__ total, unsigned long long *__restrict__ hist)
+k_accumulate_fused(Sched *sd, const u32 *__restrict__ grouped, unsigned long long *__restrict__ hist, u64 Bp, u32 shift,
+                   u32 n_buckets)
 {
-    const u64 n_items = __ldg(total);
-    const u64 n4 = n_items >> 2;
-    const u64 chunk = 256ull * 4;                       // uint4 per block iteration
-    const u64 base = (u64)blockIdx.x * chunk;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const u64 j = base + (u64)k * 256 + threadIdx.x;
-        if (j < n4) {
-            const uint4 v = __ldcs(items4 + j);
-            atomicAdd(hist + (v.x & 0x7FFFFFFFu), (v.x >> 31) ? 0x100000001ull : 1ull);
-            atomicAdd(hist + (v.y & 0x7FFFFFFFu), (v.y >> 31) ? 0x100000001ull : 1ull);
-            atomicAdd(hist + (v.z & 0x7FFFFFFFu), (v.z >> 31) ? 0x100000001ull : 1ull);
-            atomicAdd(hist + (v.w & 0x7FFFFFFFu), (v.w >> 31) ? 0x100000001ull : 1ull);
-        }
+    __shared__ u32 s_ticket;
+    const u32 tid = threadIdx.x;
+    if (tid == 0) s_ticket = atomicAdd(&sd->next_ticket, 1u);
+    __syncthreads();
+    const u32 u = s_ticket;
+    if (u >= sd->total_units) return;
+    const u32 z0 = zero_units(Bp, shift, 0, n_buckets);
+    u32 zb, zi;                                                    // zero unit zi of slice zb, or
+    bool is_zero;
+    u32 b = 0;
+    if (u < z0) { is_zero = true; zb = 0; zi = u; }
+    else {
+        u32 lo = 0, hi = n_buckets;                                // largest b with first_z[b] <= u
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (sd->first_z[mid] <= u) lo = mid; else hi = mid; }
+        b = lo;
+        const u32 fa = sd->first_a[b];
+        is_zero = u < fa;
+        zb = b + 1; zi = u - sd->first_z[b];
+        if (!is_zero) zi = u - fa;
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n_items & 3)) {   // tail
-        const u32 v = reinterpret_cast<const u32 *>(items4)[n4 * 4 + threadIdx.x];
+    if (is_zero) {
+        const u64 lo = ((u64)zb << shift) + (u64)zi * ZERO_TILE, hi = min(min(Bp, (u64)(zb + 1) << shift), lo + ZERO_TILE);
+        uint4 *dst = reinterpret_cast<uint4 *>(hist + lo);         // slices and tiles start on multiples of 64 bins
+        const u32 n16 = (u32)((hi - lo) >> 1);
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (u32 k = tid; k < n16; k += 256) dst[k] = zero;
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(&sd->zero_done[zb], 1u); }
+        return;
+    }
+    if (tid == 0) {
+        const u32 need = zero_units(Bp, shift, b, n_buckets);
+        while (*(volatile u32 *)&sd->zero_done[b] < need) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    const u64 first = (u64)sd->start[b] + (u64)zi * ACC_TILE, last = min((u64)sd->start[b] + sd->count[b], first + ACC_TILE);
+#pragma unroll 4
+    for (u64 j = first + tid; j < last; j += 256) {
+        const u32 v = __ldcs(grouped + j);
         atomicAdd(hist + (v & 0x7FFFFFFFu), (v >> 31) ? 0x100000001ull : 1ull);
     }
 }
@@ -540,6 +656,42 @@ k_cov2_base(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict_
 __device__ __forceinline__ float f32_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }   // x > 0
 __device__ __forceinline__ float f32_down(float x) { return __uint_as_float(__float_as_uint(x) - 1u); } // x > 0
 #define CUT_CHUNK 8192
+
+// valid set + -v counters (src/slimm.hpp:354-378); one CTA of 1024 threads, after both cut-offs are known
+__device__ __forceinline__ void cutoffs_valid_set(const u32 *__restrict__ stats, u32 G, u32 min_reads, const float *__restrict__ cp_all,
+                                                  u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes, DevScalars *sc)
+{
+    const u32 tid = threadIdx.x;
+    __threadfence();
+    const float c0 = *(volatile float *)&sc->cut, c1 = *(volatile float *)&sc->ucut;
+    const float *cpa = cp_all, *ucpa = cp_all + G;
+    u32 nv = 0, fc = 0, fu = 0, fm = 0, rc = 0;
+    unsigned long long pairs = 0;
+    for (u32 g0 = 0; g0 < G; g0 += 1024) {
+        const u32 g = g0 + tid;
+        bool ok = false;
+        if (g < G) {
+            const u32 reads = stats[4 * g + 1];
+            if (reads > 0) {
+                ++rc; pairs += reads;
+                const float a = __ldcg(cpa + g), b = __ldcg(ucpa + g);
+                ok = a >= c0 && b >= c1;
+                if (ok) ++nv;
+                else { fu += b < c1; fm += reads < min_reads; fc += a < c0; }
+            }
+            valid_bytes[g] = ok;
+        }
+        const u32 word = __ballot_sync(FULL, ok);
+        if ((tid & 31) == 0 && g < G) valid_bits[g >> 5] = word;
+    }
+    nv = warp_sum(nv); fc = warp_sum(fc); fu = warp_sum(fu); fm = warp_sum(fm); rc = warp_sum(rc);
+    pairs = warp_sum64(pairs);
+    if ((tid & 31) == 0) {
+        atomicAdd(&sc->n_valid, nv); atomicAdd(&sc->failed_cov, fc); atomicAdd(&sc->failed_ucov, fu);
+        atomicAdd(&sc->failed_minread, fm); atomicAdd(&sc->ref_count, rc);
+        atomicAdd(&sc->n_pairs, pairs);
+    }
+}
 
 __global__ void __launch_bounds__(1024)
 k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float q, u32 min_reads,
@@ -662,45 +814,190 @@ k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, 
     }
     __syncthreads();
     if (!s_last) return;
-    // last CTA: valid set + -v counters (src/slimm.hpp:354-378)
-    __threadfence();
-    const float c0 = *(volatile float *)&sc->cut, c1 = *(volatile float *)&sc->ucut;
-    const float *cpa = cp_all, *ucpa = cp_all + G;
-    u32 nv = 0, fc = 0, fu = 0, fm = 0, rc = 0;
-    unsigned long long pairs = 0;
-    for (u32 g0 = 0; g0 < G; g0 += 1024) {
-        const u32 g = g0 + tid;
-        bool ok = false;
-        if (g < G) {
-            const u32 reads = stats[4 * g + 1];
-            if (reads > 0) {
-                ++rc; pairs += reads;
-                const float a = __ldcg(cpa + g), b = __ldcg(ucpa + g);
-                ok = a >= c0 && b >= c1;
-                if (ok) ++nv;
-                else { fu += b < c1; fm += reads < min_reads; fc += a < c0; }
-            }
-            valid_bytes[g] = ok;
-        }
-        const u32 word = __ballot_sync(FULL, ok);
-        if ((tid & 31) == 0 && g < G) valid_bits[g >> 5] = word;
-    }
-    nv = warp_sum(nv); fc = warp_sum(fc); fu = warp_sum(fu); fm = warp_sum(fm); rc = warp_sum(rc);
-    pairs = warp_sum64(pairs);
-    if ((tid & 31) == 0) {
-        atomicAdd(&sc->n_valid, nv); atomicAdd(&sc->failed_cov, fc); atomicAdd(&sc->failed_ucov, fu);
-        atomicAdd(&sc->failed_minread, fm); atomicAdd(&sc->ref_count, rc);
-        atomicAdd(&sc->n_pairs, pairs);
-    }
+    cutoffs_valid_set(stats, G, min_reads, cp_all, valid_bits, valid_bytes, sc);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5+K6: reassignment + LCA over the same sliding windows as k_coverage.  Every lane keeps its own
-// record; a read's surviving set S = targets /\ valid is resolved with ballots restricted to the
-// read's lanes:
-//   |S| = 1 -> sole survivor (src/slimm.hpp:383-390); only reads that BECAME unique through the filter
-//              are counted here (a read with one target is already in uniq_reads_count: k_finish_assign
-//              adds valid[g] * uniq_reads_count[g] without touching the records again)
+// K4 on a thread-block cluster.  Same contract as k_cutoffs, for up to CUT_CL * CUT_SHARE references: the
+// ascending sort runs as a bitonic network over a key array DISTRIBUTED over the shared memories of the 8
+// CTAs of a cluster - compare-exchange partners further apart than one CTA's share are reached through
+// DSMEM - so no step touches L2; the two order-sensitive f32 folds stay sequential in one thread, fed from
+// shared-memory chunks staged by the whole CTA.  grid = 2 clusters (cov, uniq_cov) x 8 CTAs x 1024 threads.
+// ------------------------------------------------------------------------------------------------
+#define CUT_CL 8
+#define CUT_SHARE 32768        // keys per CTA (128 KB of dynamic shared memory)
+
+namespace cgx = cooperative_groups;
+
+__device__ __forceinline__ u32 *dsm_key(cgx::cluster_group &cl, u32 *keys, u32 idx, u32 share_log)
+{
+    return cl.map_shared_rank(keys, idx >> share_log) + (idx & ((1u << share_log) - 1u));
+}
+
+__global__ void __cluster_dims__(CUT_CL, 1, 1) __launch_bounds__(1024)
+k_cutoffs_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float q, u32 min_reads,
+                  float *__restrict__ cp_all /*[2][G]*/, u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes,
+                  DevScalars *sc)
+{
+    extern __shared__ u32 s_keys[];           // this CTA's share of the distributed key array
+    cgx::cluster_group cl = cgx::this_cluster();
+    const u32 rank = cl.block_rank();
+    const u32 which = blockIdx.x / CUT_CL;    // 0: cov, 1: uniq_cov
+    if (min_reads == 0) {                     // -mr default: 1 + (matches_count-1)/10000 (src/slimm.hpp:458-459)
+        const u32 R = (u32)sc->n_reads;
+        min_reads = R ? 1u + (R - 1u) / 10000u : 0u;
+    }
+    const u32 tid = threadIdx.x;
+    float *cp = cp_all + (size_t)which * G;
+    __shared__ u32 s_scan[1024];
+    __shared__ float s_buf[CUT_CHUNK];
+    __shared__ u32 s_base, s_i, s_n;
+    __shared__ float s_f;
+    __shared__ int s_done;
+    __shared__ bool s_last;
+
+    // cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155); the cluster shares the work
+    for (u32 g = rank * 1024 + tid; g < G; g += CUT_CL * 1024)
+        cp[g] = __fdiv_rn((float)stats[4 * g + 2 * which], (float)meta[g].y);
+    // members: references with unique reads.  Every CTA counts them (the padded size must be known everywhere)
+    u32 cnt = 0;
+    for (u32 g = tid; g < G; g += 1024) cnt += stats[4 * g + 3] > 0;
+    cnt = warp_sum(cnt);
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
+    __syncthreads();
+    const u32 n = s_n;
+    float cut = 0.0f;
+    const bool active = q < 1.0f && n > 0;    // cluster-uniform
+    u32 m = CUT_CL * 1024;                    // padded size: a power of two, at least one key per thread
+    while (m < n) m <<= 1;
+    const u32 share_log = 31 - __clz(m / CUT_CL), share = 1u << share_log;
+    if (active) {
+        for (u32 k = tid; k < share; k += 1024) s_keys[k] = 0xFFFFFFFFu;
+        if (tid == 0) { s_base = 0; s_f = 0.0f; }
+    }
+    cl.sync();                                // cp[] complete (global) and every share initialised
+    if (active && rank == 0) {
+        // total = std::accumulate(v, 0.0f) in ascending reference order; the same pass scatters the keys
+        for (u32 g0 = 0; g0 < G; g0 += 1024) {
+            const u32 g = g0 + tid;
+            const u32 keep = (g < G && stats[4 * g + 3] > 0) ? 1u : 0u;
+            const float x = keep ? __ldcg(cp + g) : 0.0f;
+            s_scan[tid] = keep;
+            __syncthreads();
+            for (u32 d = 1; d < 1024; d <<= 1) {
+                u32 t = tid >= d ? s_scan[tid - d] : 0;
+                __syncthreads();
+                s_scan[tid] += t;
+                __syncthreads();
+            }
+            const u32 base = s_base, tot = s_scan[1023];
+            if (keep) {
+                s_buf[s_scan[tid] - 1] = x;
+                *dsm_key(cl, s_keys, base + s_scan[tid] - 1, share_log) = __float_as_uint(x);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float total = s_f;
+                for (u32 k = 0; k < tot; ++k) total = __fadd_rn(total, s_buf[k]);
+                s_f = total;
+                s_base = base + tot;
+            }
+            __syncthreads();
+        }
+    }
+    if (active) {
+        cl.sync();
+        // bitonic sort, ascending (values are >= 0: u32 order == f32 order)
+        for (u32 k = 2; k <= m; k <<= 1)
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                if (j >= share) {             // partner lives in another CTA: the lower rank of the pair works
+                    const u32 prank = rank ^ (j >> share_log);
+                    if (prank > rank) {
+                        u32 *other = cl.map_shared_rank(s_keys, prank);
+                        for (u32 o = tid; o < share; o += 1024) {
+                            const u32 t = (rank << share_log) | o;
+                            const u32 a = s_keys[o], b = other[o];
+                            const bool up = (t & k) == 0;
+                            if ((a > b) == up) { s_keys[o] = b; other[o] = a; }
+                        }
+                    }
+                    cl.sync();
+                } else {
+                    for (u32 o = tid; o < share; o += 1024) {
+                        const u32 po = o ^ j;
+                        if (po > o) {
+                            const u32 t = (rank << share_log) | o;
+                            const u32 a = s_keys[o], b = s_keys[po];
+                            const bool up = (t & k) == 0;
+                            if ((a > b) == up) { s_keys[o] = b; s_keys[po] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        cl.sync();
+    }
+    if (active && rank == 0) {
+        const float total = s_f;
+        // i = n-1; while ((sub/total) < q && i > 0) { sub += v[i]; --i; }  cutoff = v[i]
+        if (tid == 0) {
+            s_done = (!(total > 0.0f) || !(q > 0.0f));   // 0/0 = NaN: NaN < q is false; q <= 0: never true
+            s_i = n - 1;
+            float s = 0.0f;
+            if (!s_done) {
+                // (sub/total) < q  <=>  sub < s*, s* = smallest f32 with fl(s*/total) >= q
+                // (x -> fl(x/total) is monotone), so the loop needs no division
+                s = __fmul_rn(q, total);
+                if (s <= 0.0f) s = __uint_as_float(1u);
+                while (__fdiv_rn(s, total) >= q && s > __uint_as_float(1u)) s = f32_down(s);
+                while (__fdiv_rn(s, total) < q) s = f32_up(s);
+            }
+            s_f = s;
+        }
+        __syncthreads();
+        const float sstar = s_f;
+        float sub = 0.0f;                                           // only thread 0's copy matters
+        u32 c_hi = n;                                               // values [c_lo, c_hi) staged, walked downwards
+        while (!s_done) {
+            const u32 c_lo = c_hi > CUT_CHUNK ? c_hi - CUT_CHUNK : 0;
+            for (u32 k = tid; k < c_hi - c_lo; k += 1024) s_buf[k] = __uint_as_float(*dsm_key(cl, s_keys, c_lo + k, share_log));
+            __syncthreads();
+            if (tid == 0) {
+                u32 i = s_i;
+                while (sub < sstar && i > 0 && i >= c_lo) {
+                    sub = __fadd_rn(sub, s_buf[i - c_lo]);
+                    --i;
+                    if (i < c_lo) break;
+                }
+                s_i = i;
+                if (!(sub < sstar) || i == 0 || c_lo == 0) s_done = 1;
+            }
+            __syncthreads();
+            c_hi = c_lo;
+        }
+        cut = __uint_as_float(*dsm_key(cl, s_keys, s_i, share_log));
+    }
+    cl.sync();                                // nobody leaves while rank 0 may still read its share
+    if (rank != 0) return;
+    if (tid == 0) {
+        if (which == 0) sc->cut = cut; else sc->ucut = cut;
+        __threadfence();
+        s_last = atomicAdd(&sc->done_ctr, 1u) == 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    cutoffs_valid_set(stats, G, min_reads, cp_all, valid_bits, valid_bytes, sc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5+K6: reassignment + LCA on the compact stream k_coverage left behind: the distinct reference ids of
+// every read with several targets, chunk by chunk (reads with one target are settled without touching
+// the records again: k_finish_assign adds valid[g] * uniq_reads_count[g]).  The same sliding windows as
+// in k_coverage, now with explicit head bits; a read's surviving set S = targets /\ valid is resolved with
+// ballots and REDUX restricted to the read's lanes:
+//   |S| = 1 -> the read BECAME unique through the filter (src/slimm.hpp:383-390)
 //   |S| >= 2 -> level-wise LCA over the 8-slot lineages, zeros included (slimm::get_lca, :516-531): the
 //              first level on which all of S agree, else slot 7 of the largest reference id;
 //              count[lca] += 1 and children[lca] U= S (phase 1 of get_reads_lca_count, :536-557),
@@ -718,156 +1015,154 @@ __device__ __forceinline__ u32 lineage_diff(const uint4 *__restrict__ lin4, u32 
            ((u32)(b.x != b0.x) << 4) | ((u32)(b.y != b0.y) << 5) | ((u32)(b.z != b0.z) << 6) | ((u32)(b.w != b0.w) << 7);
 }
 
-struct AssignOut {
-    u32 *uniq2_extra, *lca_cnt, *child_mark, *fb_mark, *cov2;
-    unsigned char *res_kind;
-    u32 *res_val;
+struct AssignParams {
+    const u32 *cw, *cw_idx; const uint2 *chunk_cnt; const u32 *lr;
+    const uint4 *meta; const uint4 *lin4; const u32 *top_idx; const u32 *vb; u32 G, half_avg; BinDiv wdiv;
+    u32 *uniq2_extra, *lca_rep, *child_mark, *fb_mark, *cov2;
+    unsigned char *res_kind; u32 *res_val;
 };
 
-__device__ __forceinline__ void mark_child(const AssignOut &o, const u32 *__restrict__ top_idx, u32 G, u32 h, bool fb, u32 level, u32 owner)
+__device__ __forceinline__ void mark_child(const AssignParams &P, u32 h, bool fb, u32 level, u32 owner)
 {
-    u32 *mk = fb ? o.fb_mark + (u64)__ldg(top_idx + owner) * G + h : o.child_mark + (u64)h * 8 + level;
+    u32 *mk = fb ? P.fb_mark + (u64)__ldg(P.top_idx + owner) * P.G + h : P.child_mark + (u64)h * 8 + level;
     if (*mk == 0) *mk = 1;
 }
 
+// a read of more than 32 records, walked by the whole warp on the original records
 template <class Rec>
-__device__ __noinline__ u64 assign_long_run(const Rec &rec, u64 p, u64 n, u32 lane, const uint4 *__restrict__ meta,
-                                            const uint4 *__restrict__ lin4, const u32 *__restrict__ top_idx,
-                                            const u32 *__restrict__ vb, u32 G, u32 half_avg, u32 w, const AssignOut &o)
+__device__ __noinline__ void assign_long_run(const Rec &rec, u32 p, u32 n, u32 lane, const AssignParams &P, u32 *lca_cnt)
 {
-    const u32 r0 = rec.read(p), gh = rec.refid(p);
-    bool have = false, multi = false, was_multi = false;
-    u32 g0 = 0, neq = 0, gmax = 0;
-    u64 lead = p, end = p;
+    const u32 r0 = rec.read(p);
+    bool have = false, multi = false;
+    u32 g0 = 0, neq = 0, gmax = 0, lead = p, end = p;
     uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0;
-    for (u64 q = p;; q += 32) {
-        const u64 i = q + lane;
+    for (u32 q = p;; q += 32) {
+        const u32 i = q + lane;
         const bool in = i < n && rec.read(i) == r0;
         const u32 inb = __ballot_sync(FULL, in);
         const u32 g = in ? rec.refid(i) : 0u;
-        const bool v = in && g < G && is_valid(vb, g);
-        was_multi |= __any_sync(FULL, in && g != gh);
+        const bool v = in && g < P.G && is_valid(P.vb, g);
         const u32 V = __ballot_sync(FULL, v);
         if (!have && V) {
             const int f = __ffs(V) - 1;
             g0 = __shfl_sync(FULL, g, f);
             lead = q + f;
-            a0 = __ldg(lin4 + 2 * (u64)g0); b0 = __ldg(lin4 + 2 * (u64)g0 + 1);
+            a0 = __ldg(P.lin4 + 2 * (u64)g0); b0 = __ldg(P.lin4 + 2 * (u64)g0 + 1);
             have = true;
         }
         if (have) {
             const bool d = v && g != g0;
-            const u32 mine = d ? lineage_diff(lin4, g, a0, b0) : 0u;
+            const u32 mine = d ? lineage_diff(P.lin4, g, a0, b0) : 0u;
             multi |= __any_sync(FULL, d);
             neq |= __reduce_or_sync(FULL, mine);
             gmax = max(gmax, __reduce_max_sync(FULL, v ? g : 0u));
         }
         if (inb != FULL) { end = q + (inb == 0 ? 0 : 32 - __clz(inb)); break; }
     }
-    if (!have) return end;
-    if (!multi) {                                                  // sole survivor
+    if (!have) return;
+    if (!multi) {                                                  // sole survivor of a read with several targets
         if (lane == 0) {
-            if (was_multi) {
-                atomicAdd(o.uniq2_extra + g0, 1u);
-                if (o.cov2) atomicAdd(o.cov2 + bin_of(meta, g0, rec.upos(lead), half_avg, w), 1u);
-            }
-            if (o.res_kind) { o.res_kind[p] = 1; o.res_val[p] = g0; }
+            atomicAdd(P.uniq2_extra + g0, 1u);
+            if (P.cov2) atomicAdd(P.cov2 + bin_of(P.meta, g0, rec.upos(lead), P.half_avg, P.wdiv), 1u);
+            if (P.res_kind) { P.res_kind[p] = 1; P.res_val[p] = g0; }
         }
-        return end;
+        return;
     }
     const u32 eq = ~neq & 0xFFu;
     const bool fb = eq == 0;                                       // no level agrees: slot 7 of the largest reference id
     const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1), owner = fb ? gmax : g0;
-    for (u64 q = p; q < end; q += 32) {                            // children[lca] U= S
-        const u64 i = q + lane;
+    for (u32 q = p; q < end; q += 32) {                            // children[lca] U= S
+        const u32 i = q + lane;
         if (i < end) {
             const u32 h = rec.refid(i);
-            if (h < G && is_valid(vb, h)) mark_child(o, top_idx, G, h, fb, level, owner);
+            if (h < P.G && is_valid(P.vb, h)) mark_child(P, h, fb, level, owner);
         }
     }
     if (lane == 0) {
-        atomicAdd(o.lca_cnt + owner * 8 + level, 1u);
-        if (o.res_kind) { o.res_kind[p] = 2; o.res_val[p] = __ldg(reinterpret_cast<const u32 *>(lin4) + (u64)owner * 8 + level); }
+        atomicAdd(lca_cnt + owner * 8 + level, 1u);
+        if (P.res_kind) { P.res_kind[p] = 2; P.res_val[p] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level); }
     }
-    return end;
 }
 
 template <class Rec>
 __global__ void __launch_bounds__(256)
-k_assign(Rec rec, u64 n, const uint4 *__restrict__ meta, const uint4 *__restrict__ lin4, const u32 *__restrict__ top_idx,
-         const u32 *__restrict__ vb, u32 G, u32 half_avg, u32 w, u32 *__restrict__ uniq2_extra, u32 *__restrict__ lca_rep,
-         u32 *__restrict__ child_mark, u32 *__restrict__ fb_mark, u32 *__restrict__ cov2,
-         unsigned char *__restrict__ res_kind, u32 *__restrict__ res_val)
+k_assign(Rec rec, u32 n, AssignParams P)
 {
     const u32 lane = threadIdx.x & 31;
-    AssignOut o{uniq2_extra, lca_rep + (u64)(blockIdx.x % LCA_REPLICAS) * 8 * G, child_mark, fb_mark, cov2, res_kind, res_val};
-    const u64 wg = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
-    u32 bad = 0;
-    for (u64 c0 = wg * CHUNK; c0 < n; c0 += nw * CHUNK) {
-        const u64 c1 = min((u64)(c0 + CHUNK), n);
-        u64 p = find_head(rec, c0, n, lane);
-        while (p < c1) {
+    u32 *lca_cnt = P.lca_rep + (u64)(blockIdx.x % LCA_REPLICAS) * 8 * P.G;
+    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (u32 c = wg; c < n_chunks; c += nw) {
+        const uint2 cnt = __ldg(P.chunk_cnt + c);
+        const u32 m = cnt.x;                                       // compact words of this chunk
+        const u32 *cw = P.cw + (u64)c * CW_SLOT;
+        u32 p = 0;
+        while (p < m) {
+            const u32 i = p + lane;
+            const bool in = i < m;
+            const u32 word = in ? __ldcs(cw + i) : 0u;
+            u32 nxw = __shfl_down_sync(FULL, word, 1);
+            if (lane == 31 && i + 1 < m) nxw = __ldcs(cw + i + 1);
+            const bool last = in && (i + 1 >= m || (nxw & CW_HEAD));
+            const u32 H = __ballot_sync(FULL, in && (word & CW_HEAD)), E = __ballot_sync(FULL, last);
             Window win;
-            load_window(rec, p, n, c1, lane, win, bad);
-            if (win.long_run) {
-                p = assign_long_run(rec, p, n, lane, meta, lin4, top_idx, vb, G, half_avg, w, o);
-                continue;
-            }
-            const u32 g = win.g;
-            const bool v = win.whole && g < G && is_valid(vb, g);
+            window_masks(H, E, min(32u, m - p), p, m, lane, in, win);   // every run is at most 32 words: none is long
+            const u32 g = word & ~CW_HEAD;
+            const bool v = win.whole && is_valid(P.vb, g);
             const u32 V = __ballot_sync(FULL, v);
-            const u32 Vm = V & win.M;                              // surviving records of my read
+            const u32 Vm = V & win.M;                              // surviving references of my read
             const int f = Vm ? __ffs(Vm) - 1 : (int)lane;
             const u32 g0 = __shfl_sync(FULL, g, f);                // first survivor in file order
-            const u32 Dm = __ballot_sync(FULL, v && g != g0);
-            const u32 gh = __shfl_sync(FULL, g, win.whole ? win.s : (int)lane);
-            const u32 Wm = __ballot_sync(FULL, win.whole && g != gh);
+            const bool d = v && g != g0;
+            const u32 Dm = __ballot_sync(FULL, d);
             const bool run_multi = (Dm & win.M) != 0;              // |S| >= 2
             const bool is_head = win.whole && (int)lane == win.s;
-            if (is_head && Vm && !run_multi) {                     // sole survivor
-                if (Wm & win.M) {                                  // it named another reference: it BECAME unique through the filter
-                    atomicAdd(o.uniq2_extra + g0, 1u);
-                    if (o.cov2) atomicAdd(o.cov2 + bin_of(meta, g0, rec.upos(p + f), half_avg, w), 1u);
+            if (is_head && Vm && !run_multi) {                     // sole survivor: the read became unique through the filter
+                atomicAdd(P.uniq2_extra + g0, 1u);
+                if (P.cw_idx) {
+                    const u32 lead = P.cw_idx[(u64)c * CW_SLOT + p + f];
+                    if (P.cov2) atomicAdd(P.cov2 + bin_of(P.meta, g0, rec.upos(lead), P.half_avg, P.wdiv), 1u);
+                    if (P.res_kind) { const u32 hd = P.cw_idx[(u64)c * CW_SLOT + i]; P.res_kind[hd] = 1; P.res_val[hd] = g0; }
                 }
-                if (o.res_kind) { o.res_kind[p + lane] = 1; o.res_val[p + lane] = g0; }
             }
             if (Dm) {                                              // some read of this window needs an LCA
-                const bool need = v && run_multi;
                 u32 mine = 0;
-                if (need && g != g0) {
-                    const uint4 a0 = __ldg(lin4 + 2 * (u64)g0), b0 = __ldg(lin4 + 2 * (u64)g0 + 1);
-                    mine = lineage_diff(lin4, g, a0, b0);
+                if (d) {
+                    const uint4 a0 = __ldg(P.lin4 + 2 * (u64)g0), b0 = __ldg(P.lin4 + 2 * (u64)g0 + 1);
+                    mine = lineage_diff(P.lin4, g, a0, b0);
                 }
-                u32 eq = 0;
-#pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    const u32 Nl = __ballot_sync(FULL, (mine >> l) & 1u);
-                    if ((Nl & win.M) == 0) eq |= 1u << l;
-                }
+                const u32 grp = win.M ? win.M : (1u << lane);      // REDUX over the lanes of my read
+                const u32 eq = ~__reduce_or_sync(grp, mine) & 0xFFu;
                 const bool fb = run_multi && eq == 0;
                 u32 owner = g0;
                 if (__any_sync(FULL, fb)) {                        // largest surviving reference id of the read
-                    u32 gm = v ? g : 0u;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const u32 t = __shfl_down_sync(FULL, gm, d);
-                        if (win.whole && (int)lane + d <= win.e) gm = max(gm, t);
-                    }
-                    const u32 top = __shfl_sync(FULL, gm, win.whole ? win.s : (int)lane);
+                    const u32 top = __reduce_max_sync(grp, v ? g : 0u);
                     if (fb) owner = top;
                 }
                 const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1);
-                if (need) mark_child(o, top_idx, G, g, fb, level, owner);
+                if (v && run_multi) mark_child(P, g, fb, level, owner);
                 const bool is_lca = is_head && run_multi;
-                if (is_lca && o.res_kind) {
-                    o.res_kind[p + lane] = 2;
-                    o.res_val[p + lane] = __ldg(reinterpret_cast<const u32 *>(lin4) + (u64)owner * 8 + level);
+                if (is_lca && P.res_kind) {
+                    const u32 hd = P.cw_idx[(u64)c * CW_SLOT + i];
+                    P.res_kind[hd] = 2;
+                    P.res_val[hd] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level);
                 }
-                warp_agg_add(o.lca_cnt, owner * 8 + level, is_lca);
+                warp_agg_add(lca_cnt, owner * 8 + level, is_lca);
             }
-            p = win.next;
+            p = win.next > p ? win.next : p + 32;
         }
+        for (u32 k = 0; k < cnt.y; ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, lca_cnt);
     }
+}
+
+// the heads of single-target reads were marked 3 by k_coverage: kind 1 with the reference when it survived
+__global__ void k_read_results_unique(unsigned char *__restrict__ res_kind, u32 *__restrict__ res_val, const u32 *__restrict__ ref,
+                                      u32 ref_stride, const u32 *__restrict__ vb, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || res_kind[i] != 3) return;
+    const u32 g = ref[(u64)i * ref_stride];
+    if (is_valid(vb, g)) { res_kind[i] = 1; res_val[i] = g; } else res_kind[i] = 0;
 }
 
 // lca_count[s] = sum of the replicas (taken apart only to spread same-address atomics)

@@ -4,6 +4,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,8 +42,11 @@ struct slimm_gpu_ctx {
     u32 *d_lca_rep = nullptr;               // [LCA_REPLICAS][G*8] spread of the LCA counters
     // bucketed scatter (histogram larger than L2)
     u32 *d_items = nullptr, *d_grouped = nullptr; u64 items_cap = 0; u32 bucket_shift = 22;
-    u32 *d_bucket_cnt = nullptr, *d_cursor = nullptr;
+    Sched *d_sched = nullptr;
+    u32 *d_cw = nullptr, *d_cw_idx = nullptr, *d_lr = nullptr; uint2 *d_chunk_cnt = nullptr; u64 cw_chunks = 0;   // compact stream for k_assign
+    BinDiv wdiv{0, 0, 0};
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
+    int cutoff_mode = -1;                   // -1 auto (cluster/DSMEM sort when it fits), 1 global-memory sort
     bool used_bucket = false;
     bool finished = false;                  // k_finish_assign ran
     std::unique_ptr<slimm_host::ProfilePlan> plan;
@@ -63,10 +68,13 @@ struct slimm_gpu_ctx {
     cudaEvent_t ev[SLIMM_GPU_T_COUNT][2] = {};
     bool ev_used[SLIMM_GPU_T_COUNT] = {};
     u64 launches = 0;
+    float tail_host_ms = 0.0f;
     std::vector<u32> h_assign;              // host copy of the assign block
     bool h_assign_ok = false;
     std::string err;
 };
+
+#define SLIMM_MAX_RECORDS 0xFFFFFF00ull
 
 static const char *k_errstr[] = {"ok", "invalid argument", "no CUDA device", "CUDA error", "out of memory",
                                  "stage called out of order", "too many records (> 2^32-1)"};
@@ -118,8 +126,19 @@ int slimm_gpu_host_alloc(void **p, uint64_t bytes)
 }
 int slimm_gpu_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? SLIMM_GPU_OK : SLIMM_GPU_ECUDA; }
 
+// {mul, s1, s2} with n / d == (t + ((n - t) >> s1)) >> s2, t = umulhi(mul, n), for every u32 n (round-up method)
+static BinDiv bin_div_for(u32 d)
+{
+    if (d == 1) return BinDiv{0, 0, 0};
+    u32 l = 0;
+    while ((1ull << l) < d) ++l;                                   // ceil(log2 d)
+    const u64 mul = ((1ull << 32) * ((1ull << l) - d)) / d + 1;
+    return BinDiv{(u32)mul, 1, l - 1};
+}
+
 static int layout_bins(slimm_gpu_ctx *ctx)
 {
+    ctx->wdiv = bin_div_for(ctx->w);
     const u32 G = ctx->G;
     ctx->h_off.assign((size_t)G + 1, 0);
     std::vector<uint4> meta(G);
@@ -189,8 +208,9 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_valid_bytes, G));
     CU(cudaMalloc(&ctx->d_assign, ctx->assign_words * 4));
     CU(cudaMalloc(&ctx->d_lca_rep, (size_t)LCA_REPLICAS * 8 * G * 4));
-    CU(cudaMalloc(&ctx->d_bucket_cnt, MAX_BUCKETS * 4));
-    CU(cudaMalloc(&ctx->d_cursor, (MAX_BUCKETS + 1) * 4));
+    CU(cudaMalloc(&ctx->d_sched, sizeof(Sched)));
+    if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
+    CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
     if (const char *e = getenv("SLIMM_GPU_SCATTER")) ctx->scatter_mode = !strcmp(e, "direct") ? 0 : !strcmp(e, "bucket") ? 1 : -1;
     CU(cudaMalloc(&ctx->d_sc, sizeof(DevScalars)));
     CU(cudaMemcpy(ctx->d_lin, ctx->h_lin.data(), (size_t)G * 32, cudaMemcpyHostToDevice));
@@ -220,7 +240,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
-    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_bucket_cnt); cudaFree(ctx->d_cursor);
+    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -274,7 +294,7 @@ int slimm_gpu_push(slimm_gpu_ctx *ctx, const uint32_t *read_id, const uint32_t *
     if (!ctx || (n && (!read_id || !ref_id || !begin_pos))) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_CREATED) return fail(ctx, SLIMM_GPU_ESTATE, "push after coverage; call slimm_gpu_reset first");
     if (ctx->external) return fail(ctx, SLIMM_GPU_ESTATE, "push after push_device");
-    if (ctx->n + n > 0xFFFFFFFFull) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-1 records");
+    if (ctx->n + n > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-256 records in one context");
     if (n == 0) return SLIMM_GPU_OK;
     CU(cudaSetDevice(ctx->device));
     int rc = reserve(ctx, ctx->n + n);
@@ -290,7 +310,7 @@ int slimm_gpu_push_device(slimm_gpu_ctx *ctx, const uint32_t *d_read_id, const u
 {
     if (!ctx || !d_read_id || !d_ref_id || !d_begin_pos) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_CREATED || ctx->n != 0) return fail(ctx, SLIMM_GPU_ESTATE, "push_device needs an empty context");
-    if (n > 0xFFFFFFFFull) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-1 records");
+    if (n > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-256 records in one context");
     free_records(ctx);
     ctx->d_rid = const_cast<u32 *>(d_read_id); ctx->d_ref = const_cast<u32 *>(d_ref_id); ctx->d_pos = const_cast<i32 *>(d_begin_pos);
     ctx->n = n; ctx->cap = n; ctx->external = true;
@@ -313,13 +333,34 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
 template <class Rec>
 static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
-    const u32 half = ctx->avg / 2u;
-    const u64 n = ctx->n;
+    const u32 n = (u32)ctx->n;
     const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
     const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 6));
+    // compact stream of the multi-mapped reads (k_assign's input), one slot per chunk
+    const bool want_idx = (ctx->flags & (SLIMM_GPU_KEEP_UNIQ_COV2 | SLIMM_GPU_READ_RESULTS)) != 0;
+    if (ctx->cw_chunks < n_chunks) {
+        cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
+        ctx->d_cw = ctx->d_cw_idx = ctx->d_lr = nullptr; ctx->d_chunk_cnt = nullptr; ctx->cw_chunks = 0;
+        CU(cudaMalloc(&ctx->d_cw, n_chunks * CW_SLOT * 4));
+        if (want_idx) CU(cudaMalloc(&ctx->d_cw_idx, n_chunks * CW_SLOT * 4));
+        CU(cudaMalloc(&ctx->d_lr, n_chunks * LR_SLOT * 4));
+        CU(cudaMalloc(&ctx->d_chunk_cnt, n_chunks * sizeof(uint2)));
+        ctx->cw_chunks = n_chunks;
+    }
+    if ((ctx->flags & SLIMM_GPU_READ_RESULTS) && ctx->res_cap < ctx->n) {
+        cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
+        ctx->d_kind = nullptr; ctx->d_val = nullptr;
+        CU(cudaMalloc(&ctx->d_kind, std::max<u64>(ctx->n, 1))); CU(cudaMalloc(&ctx->d_val, std::max<u64>(ctx->n, 1) * 4));
+        ctx->res_cap = ctx->n;
+    }
+    if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
+    CovParams P{};
+    P.meta = ctx->d_meta; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
+    P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
+    P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.sc = ctx->d_sc;
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        k_coverage<Rec, 0><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, nullptr, nullptr, 0, 0, ctx->d_sc);
+        k_coverage<Rec, 0><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
         ctx->launches++;
         CU(cudaGetLastError());
         return SLIMM_GPU_OK;
@@ -328,30 +369,34 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     const u32 n_buckets = (u32)((ctx->Bp + (1ull << shift) - 1) >> shift);
     if (ctx->items_cap < n) {
         cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); ctx->d_items = nullptr; ctx->d_grouped = nullptr;
-        CU(cudaMalloc(&ctx->d_items, ((n + 3) & ~3ull) * 4));
-        CU(cudaMalloc(&ctx->d_grouped, ((n + 3) & ~3ull) * 4));
+        CU(cudaMalloc(&ctx->d_items, (((u64)n + 3) & ~3ull) * 4));
+        CU(cudaMalloc(&ctx->d_grouped, (((u64)n + 3) & ~3ull) * 4));
         ctx->items_cap = n;
     }
     {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, MAX_BUCKETS * 4, ctx->stream));
-        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, ctx->d_meta, ctx->G, half, ctx->w, ctx->d_hist, ctx->d_items, ctx->d_bucket_cnt,
-                                                         shift, n_buckets, ctx->d_sc);
+        CU(cudaMemsetAsync(ctx->d_sched, 0, sizeof(Sched), ctx->stream));
+        P.items = ctx->d_items; P.shift = shift; P.n_buckets = n_buckets;
+        P.bucket_cnt = reinterpret_cast<u32 *>(reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count));
+        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
         ctx->launches++;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);   // the multisplit: slice starts, then group the items by slice
-        k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, ctx->d_cursor);
-        const u64 n_tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
+        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);   // the multisplit: slice starts + unit schedule, then group the items by slice
+        k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_sched, n_buckets, ctx->Bp, shift);
+        const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
-        k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_cursor, ctx->d_grouped);
+        k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped);
         ctx->launches += 2;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
-        const u64 n4 = n >> 2;
-        const u64 blocks = std::max<u64>(1, (n4 + 1023) / 1024);
-        k_accumulate<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_grouped, ctx->d_cursor + MAX_BUCKETS, ctx->d_hist);
+        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);    // zero-fill fused in: every slice is created, filled and retired in L2
+        u64 units = n / ACC_TILE + n_buckets + 1;
+        for (u32 b = 0; b < n_buckets; ++b) {
+            const u64 lo = (u64)b << shift, hi = std::min<u64>(ctx->Bp, (u64)(b + 1) << shift);
+            units += (hi - lo + ZERO_TILE - 1) / ZERO_TILE;
+        }
+        k_accumulate_fused<<<(unsigned)units, 256, 0, ctx->stream>>>(ctx->d_sched, ctx->d_grouped, ctx->d_hist, ctx->Bp, shift, n_buckets);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -360,13 +405,17 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 
 extern "C" {
 
-static int launch_coverage(slimm_gpu_ctx *ctx)
+static void choose_scatter(slimm_gpu_ctx *ctx)
 {
     // bucketed scatter when the interleaved histogram is much larger than L2 (and bin ids fit 31 bits)
     const bool big = ctx->Bp * 8 > (96ull << 20) && ctx->n >= (1u << 20);
     ctx->bucket_shift = BUCKET_SHIFT;
     while (((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift) > MAX_BUCKETS) ++ctx->bucket_shift;
-    ctx->used_bucket = ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
+    ctx->used_bucket = ctx->n > 0 && ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
+}
+
+static int launch_coverage(slimm_gpu_ctx *ctx)
+{
     if (ctx->use_sorted) return launch_coverage_t(ctx, RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted});
     return launch_coverage_t(ctx, RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos});
 }
@@ -374,7 +423,8 @@ static int launch_coverage(slimm_gpu_ctx *ctx)
 static int zero_state(slimm_gpu_ctx *ctx)
 {
     TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
-    CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
+    choose_scatter(ctx);
+    if (!ctx->used_bucket) CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
     return SLIMM_GPU_OK;
 }
@@ -481,8 +531,16 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
     }
     {
         TimeScope ts(ctx, SLIMM_GPU_T_CUTOFF);
-        k_cutoffs<<<2, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_scratch,
-                                               ctx->npow2, ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
+        if (ctx->G <= (u32)CUT_CL * CUT_SHARE && ctx->cutoff_mode != 1) {   // sort in the distributed shared memory of a cluster
+            u32 m = CUT_CL * 1024;
+            while (m < ctx->G) m <<= 1;
+            const size_t dyn = (size_t)(m / CUT_CL) * 4;
+            k_cutoffs_cluster<<<2 * CUT_CL, 1024, dyn, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp,
+                                                                      ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
+        } else {
+            k_cutoffs<<<2, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_scratch,
+                                                   ctx->npow2, ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
+        }
         ctx->launches++;
         if (ctx->d_cov2 && ctx->Bp) {   // uniq_cov2 starts as uniq_cov of the surviving references
             const u64 n_steps = ctx->Bp / 64;
@@ -502,32 +560,29 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     if (ctx->stage != ST_FILTER) return fail(ctx, SLIMM_GPU_ESTATE, "assign needs filter first");
     CU(cudaSetDevice(ctx->device));
     const u32 G = ctx->G;
-    if ((ctx->flags & SLIMM_GPU_READ_RESULTS) && ctx->res_cap < ctx->n) {
-        cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
-        ctx->d_kind = nullptr; ctx->d_val = nullptr;
-        CU(cudaMalloc(&ctx->d_kind, std::max<u64>(ctx->n, 1))); CU(cudaMalloc(&ctx->d_val, std::max<u64>(ctx->n, 1) * 4));
-        ctx->res_cap = ctx->n;
-    }
     TimeScope ts(ctx, SLIMM_GPU_T_ASSIGN);
     CU(cudaMemsetAsync(ctx->d_assign, 0, ctx->assign_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_lca_rep, 0, (size_t)LCA_REPLICAS * 8 * G * 4, ctx->stream));
-    if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
     u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     if (ctx->n) {
-        const u64 n_chunks = (ctx->n + CHUNK - 1) / CHUNK;
+        const u32 n = (u32)ctx->n;
+        const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
         const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 8));
-        const u32 half = ctx->avg / 2u;
+        AssignParams P{};
+        P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
+        P.meta = ctx->d_meta; P.lin4 = (const uint4 *)ctx->d_lin; P.top_idx = ctx->d_top_idx; P.vb = ctx->d_valid_bits;
+        P.G = G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv;
+        P.uniq2_extra = uniq2; P.lca_rep = ctx->d_lca_rep; P.child_mark = cm; P.fb_mark = fb; P.cov2 = ctx->d_cov2;
+        P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.res_val = ctx->d_val;
         if (ctx->use_sorted) {
-            RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
-            k_assign<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, (const uint4 *)ctx->d_lin, ctx->d_top_idx, ctx->d_valid_bits,
-                                                    G, half, ctx->w, uniq2, ctx->d_lca_rep, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val);
+            k_assign<<<grid, 256, 0, ctx->stream>>>(RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted}, n, P);
+            if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, (const u32 *)ctx->d_rp_sorted, 2, ctx->d_valid_bits, n);
         } else {
-            RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
-            k_assign<<<grid, 256, 0, ctx->stream>>>(rec, ctx->n, ctx->d_meta, (const uint4 *)ctx->d_lin, ctx->d_top_idx, ctx->d_valid_bits,
-                                                    G, half, ctx->w, uniq2, ctx->d_lca_rep, cm, fb, ctx->d_cov2, ctx->d_kind, ctx->d_val);
+            k_assign<<<grid, 256, 0, ctx->stream>>>(RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos}, n, P);
+            if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, ctx->d_ref, 1, ctx->d_valid_bits, n);
         }
         k_fold_lca<<<(8 * G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lca_rep, 8 * G, lca);
-        ctx->launches += 2;
+        ctx->launches += 2 + (P.res_kind ? 1 : 0);
         CU(cudaGetLastError());
     }
     ctx->stage = ST_ASSIGN;
@@ -751,6 +806,7 @@ int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off
     slimm_gpu_summary sm;
     rc = slimm_gpu_get_summary(ctx, &sm);
     if (rc) return rc;
+    const auto t_host0 = std::chrono::steady_clock::now();
     const u32 G = ctx->G;
     const u32 *uniq2 = ctx->h_assign.data(), *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     slimm_host::ProfilePlan &pl = *ctx->plan;
@@ -770,6 +826,7 @@ int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off
     *n = out.size();
     for (u64 i = 0; i < out.size() && i < cap; ++i)
         if (rows) rows[i] = out[i];
+    ctx->tail_host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     return SLIMM_GPU_OK;
 }
 
@@ -790,6 +847,7 @@ int slimm_gpu_get_timings(slimm_gpu_ctx *ctx, float *ms, int n)
     CU(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n && i < SLIMM_GPU_T_COUNT; ++i) {
         ms[i] = 0.0f;
+        if (i == SLIMM_GPU_T_TAIL_HOST) { ms[i] = ctx->tail_host_ms; continue; }
         if (ctx->timing && ctx->ev_used[i]) cudaEventElapsedTime(&ms[i], ctx->ev[i][0], ctx->ev[i][1]);
     }
     return SLIMM_GPU_OK;
