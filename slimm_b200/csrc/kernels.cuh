@@ -28,7 +28,6 @@ typedef int32_t i32;
 
 #define FULL 0xffffffffu
 #define ITEM_SKIP 0xFFFFFFFFu
-#define LCA_REPLICAS 16
 
 struct DevScalars {
     unsigned long long n_reads;   // matches_count   (partial per rank)      } summed across ranks
@@ -48,12 +47,23 @@ struct RecSoA {
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(ref + i); }
     __device__ __forceinline__ u32 upos(u32 i) const { return (u32)__ldg(pos + i); }
+    // lanes 0..2 pull the 128-byte lines that hold record i of the three arrays towards the SM
+    __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
+    {
+        const void *a = lane == 0 ? (const void *)(rid + i) : lane == 1 ? (const void *)(ref + i) : (const void *)(pos + i);
+        if (lane < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
 };
 struct RecPacked {
     const u32 *rid; const uint2 *rp;
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(&rp[i].x); }
     __device__ __forceinline__ u32 upos(u32 i) const { return __ldg(&rp[i].y); }
+    __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
+    {
+        const void *a = lane == 0 ? (const void *)(rid + i) : lane == 1 ? (const void *)(rp + i) : (const void *)(rp + i + 16);
+        if (lane < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
 };
 
 __device__ __forceinline__ u32 warp_sum(u32 v)
@@ -73,16 +83,6 @@ __device__ __forceinline__ u32 warp_or(u32 v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(FULL, v, o);
     return v;
-}
-
-// one atomic per distinct key per warp; must be reached by all 32 lanes
-__device__ __forceinline__ void warp_agg_add(u32 *base, u32 key, bool active)
-{
-    unsigned act = __ballot_sync(FULL, active);
-    if (active) {
-        unsigned peers = __match_any_sync(act, key);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(base + key, (u32)__popc(peers));
-    }
 }
 
 // padded global bin index of a record (reference src/slimm.hpp:200-201): u32 wrap of beginPos + avg/2,
@@ -174,6 +174,7 @@ __device__ __forceinline__ u32 find_head(const Rec &rec, u32 c0, u32 n, u32 lane
 }
 
 #define CHUNK 2048u          // records per warp work unit
+#define PREFETCH_AHEAD 160u  // records between a window and the lines prefetched for the windows after it
 #define CW_SLOT (CHUNK + 32) // compact words a chunk can emit (its last run may reach 31 records past the chunk)
 #define LR_SLOT 64u          // long runs a chunk can own (each is longer than 32 records)
 #define CW_HEAD 0x80000000u
@@ -251,14 +252,8 @@ __device__ __noinline__ u32 coverage_long_run(const Rec &rec, u32 p, u32 n, u32 
                 emit<MODE>(P, i, b, first, multi);
             }
         }
-        if (MODE == 1) {                                           // lanes take turns: a long run is rare
-            const u32 todo = __ballot_sync(FULL, in && ok && first);
-            for (u32 t = todo; t; t &= t - 1) {
-                const int l = __ffs(t) - 1;
-                const u32 bk = __shfl_sync(FULL, (u32)(b >> P.shift), l);
-                if (lane == 0) s_cnt[bk] += 1;
-                __syncwarp();
-            }
+        if (MODE == 1) {
+            if (in && ok && first) atomicAdd(&s_cnt[(u32)(b >> P.shift)], 1u);
             if (in && !ok) __stcs(P.items + i, ITEM_SKIP);
         }
     }
@@ -269,11 +264,10 @@ template <class Rec, int MODE>
 __global__ void __launch_bounds__(256)
 k_coverage(Rec rec, u32 n, CovParams P)
 {
-    __shared__ u32 s_cnt_all[MODE ? 8 * MAX_BUCKETS : 1];          // warp-private slice counters: no atomics
+    __shared__ u32 s_cnt[MODE ? MAX_BUCKETS : 1];                  // items per histogram slice (shared-memory REDs)
     __shared__ u32 s_h, s_u, s_b;
-    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    u32 *s_cnt = s_cnt_all + (MODE ? wid * MAX_BUCKETS : 0);
-    if (MODE) for (u32 b = tid; b < 8 * MAX_BUCKETS; b += 256) s_cnt_all[b] = 0;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    if (MODE) for (u32 b = tid; b < MAX_BUCKETS; b += 256) s_cnt[b] = 0;
     if (tid == 0) { s_h = 0; s_u = 0; s_b = 0; }
     __syncthreads();
     u32 heads = 0, uniq = 0, bad = 0;
@@ -299,8 +293,12 @@ k_coverage(Rec rec, u32 n, CovParams P)
             const bool is_head = win.whole && (int)lane == win.s;
             bool first = is_head;
             if (Wm) {                                              // some read with several references: repeat hits need a look
-                const u32 same = __match_any_sync(FULL, win.whole ? g : ~lane);
-                if (multi) first = (same & win.M & LANE_LT(lane)) == 0;
+                if (multi) first = true;
+                const int span = (int)__reduce_max_sync(FULL, multi ? (u32)(win.e - win.s) : 0u);
+                for (int d = 1; d <= span; ++d) {                  // the same reference earlier in my read?
+                    const u32 t = __shfl_up_sync(FULL, g, d);
+                    if (multi && (int)lane - d >= win.s && t == g) first = false;
+                }
                 const u32 C = __ballot_sync(FULL, multi && first); // the compact stream keeps the distinct references
                 if (multi && first) {
                     const u64 at = cw_base + n_cw + __popc(C & LANE_LT(lane));
@@ -323,16 +321,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
                     emit<MODE>(P, p + lane, b, first, multi);
                 }
             }
-            if (MODE == 1) {
-                const bool cnt = win.whole && ok && first;
-                const u32 act = __ballot_sync(FULL, cnt);
-                if (cnt) {
-                    const u32 bk = (u32)(b >> P.shift);
-                    const u32 peers = __match_any_sync(act, bk);
-                    if ((int)lane == __ffs(peers) - 1) s_cnt[bk] += __popc(peers);
-                }
-                __syncwarp();
-            }
+            if (MODE == 1 && win.whole && ok && first) atomicAdd(&s_cnt[(u32)(b >> P.shift)], 1u);
             p = win.next;
         }
         if (lane == 0) P.chunk_cnt[c] = make_uint2(n_cw, n_lr);
@@ -341,12 +330,8 @@ k_coverage(Rec rec, u32 n, CovParams P)
     if (lane == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
     __syncthreads();
     if (MODE)
-        for (u32 b = tid; b < P.n_buckets; b += 256) {
-            u32 c = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c += s_cnt_all[k * MAX_BUCKETS + b];
-            if (c) atomicAdd(P.bucket_cnt + b, c);
-        }
+        for (u32 b = tid; b < P.n_buckets; b += 256)
+            if (s_cnt[b]) atomicAdd(P.bucket_cnt + b, s_cnt[b]);
     if (tid == 0) {
         if (s_h) atomicAdd(&P.sc->n_reads, (unsigned long long)s_h);
         if (s_u) atomicAdd(&P.sc->n_uniq, (unsigned long long)s_u);
@@ -354,125 +339,75 @@ k_coverage(Rec rec, u32 n, CovParams P)
     }
 }
 
-// Schedule of the fused zero + accumulate kernel, built on the device from the slice sizes.  Work units are
-// handed out in this order (tickets): Z(0), then for every slice b: Z(b+1), A(b).  Z(b) zero-fills slice b of
-// the histogram (ZERO_TILE bins per unit), A(b) applies ACC_TILE of the slice's items.  A(b) only waits for
-// Z(b), which was handed out a whole slice earlier.
-#define ZERO_TILE 8192u      // bins per zero unit (64 KB of interleaved u64)
-#define ACC_TILE 4096u       // items per accumulate unit
+// Per-slice bookkeeping shared by k_coverage (count), k_bucket_scan, k_split (cursor) and k_accumulate.
 struct Sched {
-    u32 next_ticket, total_units, total_items, pad;
+    u32 total_items, pad[3];
     u32 cursor[MAX_BUCKETS];     // k_split's write cursors (start of every slice's items, advanced by the split)
     u32 start[MAX_BUCKETS];      // start of every slice's items
     u32 count[MAX_BUCKETS];      // items per slice (filled by k_coverage)
-    u32 first_z[MAX_BUCKETS];    // ticket of the first unit of Z(b+1)
-    u32 first_a[MAX_BUCKETS];    // ticket of the first unit of A(b)
-    u32 zero_done[MAX_BUCKETS];  // finished units of Z(b)
 };
 
-__device__ __forceinline__ u32 zero_units(u64 Bp, u32 shift, u32 b, u32 n_buckets)
+// exclusive scan of the slice sizes -> item starts / write cursors (one block)
+__global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_buckets)
 {
-    if (b >= n_buckets) return 0;
-    const u64 lo = (u64)b << shift, hi = min(Bp, (u64)(b + 1) << shift);
-    return (u32)((hi - lo + ZERO_TILE - 1) / ZERO_TILE);
-}
-
-// exclusive scan of the slice sizes -> item starts / write cursors and the unit schedule (one block)
-__global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_buckets, u64 Bp, u32 shift)
-{
-    __shared__ u32 s[MAX_BUCKETS], s2[MAX_BUCKETS];
+    __shared__ u32 s[MAX_BUCKETS];
     const u32 tid = threadIdx.x;
     const u32 v = tid < n_buckets ? sd->count[tid] : 0;
-    const u32 units = tid < n_buckets ? zero_units(Bp, shift, tid + 1, n_buckets) + (v + ACC_TILE - 1) / ACC_TILE : 0;
-    s[tid] = v; s2[tid] = units;
+    s[tid] = v;
     __syncthreads();
     for (u32 d = 1; d < MAX_BUCKETS; d <<= 1) {
-        const u32 t = tid >= d ? s[tid - d] : 0, t2 = tid >= d ? s2[tid - d] : 0;
+        const u32 t = tid >= d ? s[tid - d] : 0;
         __syncthreads();
-        s[tid] += t; s2[tid] += t2;
+        s[tid] += t;
         __syncthreads();
     }
-    if (tid < n_buckets) {
-        sd->cursor[tid] = sd->start[tid] = s[tid] - v;
-        const u32 z0 = zero_units(Bp, shift, 0, n_buckets);
-        sd->first_z[tid] = z0 + s2[tid] - units;
-        sd->first_a[tid] = z0 + s2[tid] - units + zero_units(Bp, shift, tid + 1, n_buckets);
-        sd->zero_done[tid] = 0;
-    }
-    if (tid == MAX_BUCKETS - 1) {
-        sd->total_items = s[tid];                                 // records minus repeat hits
-        sd->total_units = zero_units(Bp, shift, 0, n_buckets) + s2[tid];
-        sd->next_ticket = 0;
-    }
+    if (tid < n_buckets) sd->cursor[tid] = sd->start[tid] = s[tid] - v;
+    if (tid == MAX_BUCKETS - 1) sd->total_items = s[tid];          // records minus repeat hits
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1b multisplit: groups the items by histogram slice.  A CTA ranks a tile of 256 x SPLIT_ITEMS items
-// with warp-private counters (MATCH.ANY inside the warp, plain shared-memory read-modify-write by the
-// group leader: no shared atomics), orders the tile by slice in shared memory and copies every slice's
-// share to its reserved place in the output, so the global stores are runs of consecutive words.
+// K1b multisplit: groups the items by histogram slice.  A CTA ranks a tile of 256 x SPLIT_ITEMS items with
+// one returning shared-memory atomic per item (measured on B200: they run at streaming-read speed, while
+// MATCH.ANY over ~400 distinct slices is 8x slower), orders the tile by slice in shared memory and copies
+// every slice's share to its reserved place in the output, so the global stores are runs of consecutive words.
 // ------------------------------------------------------------------------------------------------
 #define SPLIT_ITEMS 16
 #define SPLIT_TILE (256 * SPLIT_ITEMS)
 __global__ void __launch_bounds__(256)
 k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out)
 {
-    __shared__ u32 s_cnt[8 * MAX_BUCKETS];     // per warp: items of each slice, then the warp's offset inside the slice
-    __shared__ u32 s_off[MAX_BUCKETS];         // tile-local start of each slice
+    __shared__ u32 s_cnt[MAX_BUCKETS];         // items of each slice in this tile, then the slice's tile-local start
     __shared__ u32 s_delta[MAX_BUCKETS];       // global start - tile-local start (mod 2^32)
     __shared__ u32 s_item[SPLIT_TILE];
     __shared__ unsigned short s_bkt[SPLIT_TILE];
     __shared__ u32 s_warp_tot[8];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    u32 *my_cnt = s_cnt + wid * MAX_BUCKETS;
-    const u64 n_tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (u32 b = tid; b < 8 * MAX_BUCKETS; b += 256) s_cnt[b] = 0;
+        for (u32 b = tid; b < MAX_BUCKETS; b += 256) s_cnt[b] = 0;
         __syncthreads();
         const u64 t0 = tile * SPLIT_TILE;
-        u32 item[SPLIT_ITEMS], where[SPLIT_ITEMS];             // where: slice << 16 | slot inside (warp, slice)
+        u32 item[SPLIT_ITEMS], where[SPLIT_ITEMS];             // where: slice << 16 | rank inside (tile, slice)
 #pragma unroll
         for (int k = 0; k < SPLIT_ITEMS; ++k) {
             const u64 i = t0 + (u64)k * 256 + tid;
             item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
         }
-        u32 peers[SPLIT_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k) {                // the MATCHes are independent: all of them in flight at once
-            const bool active = item[k] != ITEM_SKIP;
-            const u32 act = __ballot_sync(FULL, active);
-            peers[k] = 0;
-            if (active) peers[k] = __match_any_sync(act, (item[k] & 0x7FFFFFFFu) >> shift);
-        }
-#pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k) {                // ordered updates of the warp's counters
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
             where[k] = 0xFFFFFFFFu;
-            if (peers[k]) {
+            if (item[k] != ITEM_SKIP) {
                 const u32 bk = (item[k] & 0x7FFFFFFFu) >> shift;
-                const int leader = __ffs(peers[k]) - 1;
-                u32 old = 0;
-                if ((int)lane == leader) { old = my_cnt[bk]; my_cnt[bk] = old + __popc(peers[k]); }
-                old = __shfl_sync(peers[k], old, leader);
-                where[k] = (bk << 16) | (old + __popc(peers[k] & LANE_LT(lane)));
+                where[k] = (bk << 16) | atomicAdd(&s_cnt[bk], 1u);
             }
-            __syncwarp();
         }
         __syncthreads();
-        // per slice: offsets of the 8 warps, tile total; then the exclusive scan over slices
-        u32 tot[2];
+        // exclusive scan of the slice counts over the tile (two slices per thread, halves in order)
+        u32 tot[2], excl[2], base = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const u32 b = tid + h * 256;
-            u32 run = 0;
-            if (b < n_buckets) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { const u32 c = s_cnt[k * MAX_BUCKETS + b]; s_cnt[k * MAX_BUCKETS + b] = run; run += c; }
-            }
-            tot[h] = run;
-        }
-        u32 excl[2], base = 0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                          // block-wide exclusive scan of tot[h] over tid, halves in order
+            tot[h] = b < n_buckets ? s_cnt[b] : 0u;
             u32 x = tot[h];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
@@ -489,7 +424,7 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
         for (int h = 0; h < 2; ++h) {
             const u32 b = tid + h * 256;
             if (b < n_buckets) {
-                s_off[b] = excl[h];
+                s_cnt[b] = excl[h];
                 if (tot[h]) s_delta[b] = atomicAdd(&sd->cursor[b], tot[h]) - excl[h];
             }
         }
@@ -498,7 +433,7 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
         for (int k = 0; k < SPLIT_ITEMS; ++k)
             if (where[k] != 0xFFFFFFFFu) {
                 const u32 bk = where[k] >> 16;
-                const u32 pos = s_off[bk] + my_cnt[bk] + (where[k] & 0xFFFFu);
+                const u32 pos = s_cnt[bk] + (where[k] & 0xFFFFu);
                 s_item[pos] = item[k];
                 s_bkt[pos] = (unsigned short)bk;
             }
@@ -510,56 +445,31 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 fused zero-fill + accumulate.  One launch; every CTA draws a ticket and looks its unit up in the
-// schedule.  A slice is zero-filled in L2 (full-sector stores, no HBM read), its items are applied as
-// 64-bit REDs that all hit L2, and the slice leaves for HBM once: the random read-modify-writes never
-// miss.  Tickets are handed out in order, so the Z(b) units an A(b) unit waits for are always running.
+// K2 accumulate: applies the grouped items in stream order, one 64-bit RED each: the CTAs in flight work
+// on one or two adjacent histogram slices, so the REDs meet in L2 and a slice's sectors travel HBM -> L2 ->
+// HBM once.  (Zero-filling the slices in L2 right before their REDs - one fused persistent kernel with
+// zeroer and accumulator CTAs - was measured too, scripts/micro/fused_bench.cu: no faster than this kernel
+// behind a memset, and the memset overlaps k_coverage / k_split on a second stream for free.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_accumulate_fused(Sched *sd, const u32 *__restrict__ grouped, unsigned long long *__restrict__ hist, u64 Bp, u32 shift,
-                   u32 n_buckets)
+k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsigned long long *__restrict__ hist, u32 per_block)
 {
-    __shared__ u32 s_ticket;
-    const u32 tid = threadIdx.x;
-    if (tid == 0) s_ticket = atomicAdd(&sd->next_ticket, 1u);
-    __syncthreads();
-    const u32 u = s_ticket;
-    if (u >= sd->total_units) return;
-    const u32 z0 = zero_units(Bp, shift, 0, n_buckets);
-    u32 zb, zi;                                                    // zero unit zi of slice zb, or
-    bool is_zero;
-    u32 b = 0;
-    if (u < z0) { is_zero = true; zb = 0; zi = u; }
-    else {
-        u32 lo = 0, hi = n_buckets;                                // largest b with first_z[b] <= u
-        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (sd->first_z[mid] <= u) lo = mid; else hi = mid; }
-        b = lo;
-        const u32 fa = sd->first_a[b];
-        is_zero = u < fa;
-        zb = b + 1; zi = u - sd->first_z[b];
-        if (!is_zero) zi = u - fa;
-    }
-    if (is_zero) {
-        const u64 lo = ((u64)zb << shift) + (u64)zi * ZERO_TILE, hi = min(min(Bp, (u64)(zb + 1) << shift), lo + ZERO_TILE);
-        uint4 *dst = reinterpret_cast<uint4 *>(hist + lo);         // slices and tiles start on multiples of 64 bins
-        const u32 n16 = (u32)((hi - lo) >> 1);
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        for (u32 k = tid; k < n16; k += 256) dst[k] = zero;
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(&sd->zero_done[zb], 1u); }
+    const u32 n_items = sd->total_items;
+    if (per_block == 0) {                                          // grid-stride
+        const u32 stride = gridDim.x * blockDim.x;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items && i + stride > i; i += stride) {
+            const u32 v = __ldcs(grouped + i);
+            atomicAdd(hist + (v & 0x7FFFFFFFu), (v >> 31) ? 0x100000001ull : 1ull);
+        }
         return;
     }
-    if (tid == 0) {
-        const u32 need = zero_units(Bp, shift, b, n_buckets);
-        while (*(volatile u32 *)&sd->zero_done[b] < need) __nanosleep(64);
-        __threadfence();
-    }
-    __syncthreads();
-    const u64 first = (u64)sd->start[b] + (u64)zi * ACC_TILE, last = min((u64)sd->start[b] + sd->count[b], first + ACC_TILE);
-#pragma unroll 4
-    for (u64 j = first + tid; j < last; j += 256) {
-        const u32 v = __ldcs(grouped + j);
-        atomicAdd(hist + (v & 0x7FFFFFFFu), (v >> 31) ? 0x100000001ull : 1ull);
+    const u64 first = (u64)blockIdx.x * per_block, last = min((u64)n_items, first + per_block);   // a block owns consecutive items
+    for (u64 j0 = first; j0 < last; j0 += 256 * 8) {
+        u32 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const u64 j = j0 + (u64)k * 256 + threadIdx.x; v[k] = j < last ? __ldcs(grouped + j) : ITEM_SKIP; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (v[k] != ITEM_SKIP) atomicAdd(hist + (v[k] & 0x7FFFFFFFu), (v[k] >> 31) ? 0x100000001ull : 1ull);
     }
 }
 
@@ -656,6 +566,28 @@ k_cov2_base(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict_
 __device__ __forceinline__ float f32_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }   // x > 0
 __device__ __forceinline__ float f32_down(float x) { return __uint_as_float(__float_as_uint(x) - 1u); } // x > 0
 #define CUT_CHUNK 8192
+
+// The descending walk of get_quantile_cut_off over the staged values buf[k] = v[c_lo + k]:
+//   while (sub < sstar && i > 0) { sub += v[i]; --i; }   restricted to indices >= c_lo.
+// Eight values are loaded up front and their running sums formed back to back, so the only serial chain is
+// the f32 additions themselves (the sums are the same left-to-right sums, rounded once per addition).
+__device__ __forceinline__ void walk_chunk(const float *buf, u32 c_lo, u32 &i, float &sub, float sstar)
+{
+    const u32 stop = max(c_lo, 1u);                                // index 0 is never added
+    while (i >= stop) {
+        const u32 m = min(i - stop + 1u, 8u);
+        float pre[9];
+        pre[0] = sub;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pre[k + 1] = __fadd_rn(pre[k], k < (int)m ? buf[i - k - c_lo] : 0.0f);
+        u32 take = m;                                              // first k with !(pre[k] < sstar): v[i - k] is not added
+#pragma unroll
+        for (int k = 7; k >= 0; --k) if (k < (int)m && !(pre[k] < sstar)) take = k;
+        sub = pre[take];
+        i -= take;
+        if (take < m) return;
+    }
+}
 
 // valid set + -v counters (src/slimm.hpp:354-378); one CTA of 1024 threads, after both cut-offs are known
 __device__ __forceinline__ void cutoffs_valid_set(const u32 *__restrict__ stats, u32 G, u32 min_reads, const float *__restrict__ cp_all,
@@ -794,11 +726,7 @@ k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, 
             __syncthreads();
             if (tid == 0) {
                 u32 i = s_i;
-                while (sub < sstar && i > 0 && i >= c_lo) {
-                    sub = __fadd_rn(sub, s_buf[i - c_lo]);
-                    --i;
-                    if (i < c_lo) break;
-                }
+                walk_chunk(s_buf, c_lo, i, sub, sstar);
                 s_i = i;
                 if (!(sub < sstar) || i == 0 || c_lo == 0) s_done = 1;
             }
@@ -966,11 +894,7 @@ k_cutoffs_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta,
             __syncthreads();
             if (tid == 0) {
                 u32 i = s_i;
-                while (sub < sstar && i > 0 && i >= c_lo) {
-                    sub = __fadd_rn(sub, s_buf[i - c_lo]);
-                    --i;
-                    if (i < c_lo) break;
-                }
+                walk_chunk(s_buf, c_lo, i, sub, sstar);
                 s_i = i;
                 if (!(sub < sstar) || i == 0 || c_lo == 0) s_done = 1;
             }
@@ -1018,7 +942,7 @@ __device__ __forceinline__ u32 lineage_diff(const uint4 *__restrict__ lin4, u32 
 struct AssignParams {
     const u32 *cw, *cw_idx; const uint2 *chunk_cnt; const u32 *lr;
     const uint4 *meta; const uint4 *lin4; const u32 *top_idx; const u32 *vb; u32 G, half_avg; BinDiv wdiv;
-    u32 *uniq2_extra, *lca_rep, *child_mark, *fb_mark, *cov2;
+    u32 *uniq2_extra, *lca_cnt, *child_mark, *fb_mark, *cov2;
     unsigned char *res_kind; u32 *res_val;
 };
 
@@ -1028,9 +952,21 @@ __device__ __forceinline__ void mark_child(const AssignParams &P, u32 h, bool fb
     if (*mk == 0) *mk = 1;
 }
 
+// count[lca] += 1 through a small direct-mapped cache in shared memory: a taxon that dominates the sample
+// costs one global atomic per CTA instead of one per read
+#define LCA_CACHE 2048
+#define LCA_EMPTY 0xFFFFFFFFu
+__device__ __forceinline__ void count_lca(u32 *s_key, u32 *s_val, u32 *__restrict__ lca_cnt, u32 key)
+{
+    const u32 slot = (key * 2654435761u) >> 21;
+    const u32 old = atomicCAS(&s_key[slot], LCA_EMPTY, key);
+    if (old == LCA_EMPTY || old == key) atomicAdd(&s_val[slot], 1u);
+    else atomicAdd(lca_cnt + key, 1u);
+}
+
 // a read of more than 32 records, walked by the whole warp on the original records
 template <class Rec>
-__device__ __noinline__ void assign_long_run(const Rec &rec, u32 p, u32 n, u32 lane, const AssignParams &P, u32 *lca_cnt)
+__device__ __noinline__ void assign_long_run(const Rec &rec, u32 p, u32 n, u32 lane, const AssignParams &P, u32 *s_key, u32 *s_val)
 {
     const u32 r0 = rec.read(p);
     bool have = false, multi = false;
@@ -1079,7 +1015,7 @@ __device__ __noinline__ void assign_long_run(const Rec &rec, u32 p, u32 n, u32 l
         }
     }
     if (lane == 0) {
-        atomicAdd(lca_cnt + owner * 8 + level, 1u);
+        count_lca(s_key, s_val, P.lca_cnt, owner * 8 + level);
         if (P.res_kind) { P.res_kind[p] = 2; P.res_val[p] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level); }
     }
 }
@@ -1088,8 +1024,10 @@ template <class Rec>
 __global__ void __launch_bounds__(256)
 k_assign(Rec rec, u32 n, AssignParams P)
 {
+    __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
     const u32 lane = threadIdx.x & 31;
-    u32 *lca_cnt = P.lca_rep + (u64)(blockIdx.x % LCA_REPLICAS) * 8 * P.G;
+    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
+    __syncthreads();
     const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
     const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 c = wg; c < n_chunks; c += nw) {
@@ -1100,6 +1038,7 @@ k_assign(Rec rec, u32 n, AssignParams P)
         while (p < m) {
             const u32 i = p + lane;
             const bool in = i < m;
+            if (lane == 0 && p + PREFETCH_AHEAD < m) asm volatile("prefetch.global.L1 [%0];" ::"l"(cw + p + PREFETCH_AHEAD));
             const u32 word = in ? __ldcs(cw + i) : 0u;
             u32 nxw = __shfl_down_sync(FULL, word, 1);
             if (lane == 31 && i + 1 < m) nxw = __ldcs(cw + i + 1);
@@ -1147,12 +1086,15 @@ k_assign(Rec rec, u32 n, AssignParams P)
                     P.res_kind[hd] = 2;
                     P.res_val[hd] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level);
                 }
-                warp_agg_add(lca_cnt, owner * 8 + level, is_lca);
+                if (is_lca) count_lca(s_key, s_val, P.lca_cnt, owner * 8 + level);
             }
             p = win.next > p ? win.next : p + 32;
         }
-        for (u32 k = 0; k < cnt.y; ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, lca_cnt);
+        for (u32 k = 0; k < cnt.y; ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, s_key, s_val);
     }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x)
+        if (s_key[k] != LCA_EMPTY && s_val[k]) atomicAdd(P.lca_cnt + s_key[k], s_val[k]);
 }
 
 // the heads of single-target reads were marked 3 by k_coverage: kind 1 with the reference when it survived
@@ -1163,17 +1105,6 @@ __global__ void k_read_results_unique(unsigned char *__restrict__ res_kind, u32 
     if (i >= n || res_kind[i] != 3) return;
     const u32 g = ref[(u64)i * ref_stride];
     if (is_valid(vb, g)) { res_kind[i] = 1; res_val[i] = g; } else res_kind[i] = 0;
-}
-
-// lca_count[s] = sum of the replicas (taken apart only to spread same-address atomics)
-__global__ void k_fold_lca(const u32 *__restrict__ lca_rep, u32 n_slots, u32 *__restrict__ lca_cnt)
-{
-    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slots) return;
-    u32 v = 0;
-#pragma unroll
-    for (int r = 0; r < LCA_REPLICAS; ++r) v += lca_rep[(u64)r * n_slots + s];
-    lca_cnt[s] = v;
 }
 
 // uniq_reads_count2[g] = (valid[g] ? uniq_reads_count[g] : 0) + reads that became unique;

@@ -7,8 +7,9 @@
 // The reference keeps unordered_map<taxon, count> and unordered_map<taxon, std::set<ref>>.  Here every
 // taxon that can occur is a value of the [G,8] lineage table, so a plan built once per database maps
 // lineage slots to dense taxon indices and all per-sample state lives in flat arrays; sets of
-// contributing references are sorted vectors merged lazily, and only collected for taxa whose set is
-// ever read (taxa with direct counts, the requested rank and its parent rank, strain level).
+// contributing references are plain vectors that are de-duplicated lazily with a stamp array (only set
+// semantics, the smallest and the largest member are ever read: no sort), and only collected for taxa
+// whose set is ever read (taxa with direct counts, the requested rank and its parent rank, strain level).
 // The reference walks its snapshot of direct counts in libstdc++ hash order; here the order is
 // ascending (rank, taxon) - identical results whenever the lineage table is tree-consistent
 // (SURVEY.md appendix A8).
@@ -41,6 +42,7 @@ ProfilePlan::ProfilePlan(u32 n_refs, const u32 *ref_len, const u32 *lineage, u64
     count.assign(T, 0); direct.assign(T, 0); has_count.assign(T, 0); dirty.assign(T, 0); seen.assign(T, 0);
     kids.resize(T);
     pab.assign(T, 0.0f); sab.assign(T, 0.0f); pcnt.assign(T, 0); scnt.assign(T, 0); has_p.assign(T, 0); has_s.assign(T, 0);
+    stamp.assign(G, 0); kmin.assign(T, 0xFFFFFFFFu); kmax.assign(T, 0);
 }
 
 int ProfilePlan::find(u32 taxon) const
@@ -58,8 +60,13 @@ void ProfilePlan::normalize(u32 t)
 {
     if (!dirty[t]) return;
     std::vector<u32> &k = kids[t];
-    std::sort(k.begin(), k.end());
-    k.erase(std::unique(k.begin(), k.end()), k.end());
+    if (++epoch == 0) { std::fill(stamp.begin(), stamp.end(), 0u); epoch = 1; }
+    size_t m = 0;
+    u32 lo = 0xFFFFFFFFu, hi = 0;
+    for (u32 r : k)
+        if (stamp[r] != epoch) { stamp[r] = epoch; k[m++] = r; lo = std::min(lo, r); hi = std::max(hi, r); }
+    k.resize(m);
+    kmin[t] = lo; kmax[t] = hi;
     dirty[t] = 0;
 }
 
@@ -84,8 +91,7 @@ void ProfilePlan::add_child(u32 t, u32 ref)
 {
     touch(t);
     std::vector<u32> &k = kids[t];
-    if (!k.empty() && k.back() > ref) dirty[t] = 1;
-    if (k.empty() || k.back() != ref) k.push_back(ref);
+    if (k.empty() || k.back() != ref) { k.push_back(ref); dirty[t] = 1; }
 }
 
 int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
@@ -104,12 +110,15 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
         normalize(t);
         if (kids[t].empty()) return SLIMM_GPU_EINVAL;            // .at() would throw in the reference
         tmp = kids[t];                                           // copied before the loop (:575)
-        const u32 f = tmp[0], c = direct[t];
+        const u32 f = kmin[t], c = direct[t];
         for (u32 j = rank[t] + 1; j < 8; ++j) {
             const u32 rc = slot_t[(size_t)f * 8 + j];
             touch(rc);
             count[rc] += c; has_count[rc] = 1;
-            if (need_kids(rc)) { kids[rc].insert(kids[rc].end(), tmp.begin(), tmp.end()); dirty[rc] = 1; }
+            if (need_kids(rc)) {
+                kids[rc].insert(kids[rc].end(), tmp.begin(), tmp.end()); dirty[rc] = 1;
+                if (kids[rc].size() > 4 * (size_t)G + 64) normalize(rc);
+            }
         }
     }
     // phase 3 (:589-610): uniquely (re)assigned reads up each reference's own lineage
@@ -128,6 +137,7 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
                 k.push_back(g);
                 k.insert(k.end(), k0.begin(), k0.end());
                 dirty[rc] = 1;
+                if (k.size() > 4 * (size_t)G + 64) normalize(rc);
             }
         }
     }
@@ -151,12 +161,12 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
         gl /= (u32)k.size();
         const float cov = (float)(u32)(count[t] * avg_read_length) / gl;   // u32 product (:792)
         const float ab = (float)count[t] / R * 100;
-        const u32 p = slot_t[(size_t)k.back() * 8 + pr];           // lineage of the last child iterated
+        const u32 p = slot_t[(size_t)kmax[t] * 8 + pr];            // lineage of the last child iterated (std::set order)
         if (!has_s[p]) { has_s[p] = 1; sab[p] = ab; scnt[p] = count[t]; parents.push_back(p); touch(p); }
         else { sab[p] += ab; scnt[p] += count[t]; }
         if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) continue;
         slimm_profile_row r;
-        r.taxon = vals[t]; r.kind = 0; r.read_count = count[t]; r.first_child = k[0]; r.abundance = ab;
+        r.taxon = vals[t]; r.kind = 0; r.read_count = count[t]; r.first_child = kmin[t]; r.abundance = ab;
         out.push_back(r);
         sum_ab += ab;
         sum_cnt += count[t];
@@ -168,7 +178,7 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
         if (uab > abundance_cut_off && named[p]) {
             slimm_profile_row r;
             r.taxon = vals[p]; r.kind = 1; r.read_count = ucnt; r.abundance = uab; r.first_child = 0xFFFFFFFFu;
-            if (vals[p] != 0) { normalize(p); if (!kids[p].empty()) r.first_child = kids[p][0]; }
+            if (vals[p] != 0) { normalize(p); if (!kids[p].empty()) r.first_child = kmin[p]; }
             out.push_back(r);
             sum_cnt += ucnt;
             sum_ab += uab;

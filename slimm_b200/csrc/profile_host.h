@@ -24,13 +24,15 @@ struct ProfilePlan {
     std::vector<uint8_t> has_count, dirty, seen, has_p, has_s;
     std::vector<std::vector<u32>> kids;
     std::vector<u32> touched, snapshot;
+    std::vector<u32> stamp, kmin, kmax;   // duplicate filter over references; smallest / largest member of a normalized set
+    u32 epoch = 0;
 
     ProfilePlan(u32 n_refs, const u32 *ref_len, const u32 *lineage, u64 n_taxa, const u32 *taxa_id,
                 const uint8_t *taxa_rank, const uint8_t *taxa_has_name);
     int find(u32 taxon) const;
     void begin();
     void add_direct(u32 t, u32 c);      // t: dense index
-    void add_child(u32 t, u32 ref);     // (t, ref) in ascending order keeps the sets sorted for free
+    void add_child(u32 t, u32 ref);
     int finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
                float abundance_cut_off, u32 rank, std::vector<slimm_profile_row> &out);
 

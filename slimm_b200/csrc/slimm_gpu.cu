@@ -25,7 +25,8 @@ enum { ST_CREATED = 0, ST_COVERAGE = 1, ST_FILTER = 2, ST_ASSIGN = 3 };
 
 struct slimm_gpu_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t zero_start = nullptr, zero_done = nullptr;
     bool own_stream = true;
     cudaEvent_t upload_done = nullptr;
     u32 G = 0, w = 0, avg = 0, flags = 0, n_top = 0, npow2 = 1;
@@ -39,7 +40,6 @@ struct slimm_gpu_ctx {
     u32 *d_stats = nullptr; float *d_cp = nullptr; u32 *d_scratch = nullptr;
     u32 *d_valid_bits = nullptr; unsigned char *d_valid_bytes = nullptr;
     u32 *d_assign = nullptr; u64 assign_words = 0;
-    u32 *d_lca_rep = nullptr;               // [LCA_REPLICAS][G*8] spread of the LCA counters
     // bucketed scatter (histogram larger than L2)
     u32 *d_items = nullptr, *d_grouped = nullptr; u64 items_cap = 0; u32 bucket_shift = 22;
     Sched *d_sched = nullptr;
@@ -179,6 +179,9 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->zero_start, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->zero_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { CU(cudaEventCreate(&ctx->ev[i][0])); CU(cudaEventCreate(&ctx->ev[i][1])); }
     const u32 G = ctx->G = cfg->n_refs;
@@ -207,7 +210,6 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_valid_bits, ((size_t)G + 31) / 32 * 4 + 4));
     CU(cudaMalloc(&ctx->d_valid_bytes, G));
     CU(cudaMalloc(&ctx->d_assign, ctx->assign_words * 4));
-    CU(cudaMalloc(&ctx->d_lca_rep, (size_t)LCA_REPLICAS * 8 * G * 4));
     CU(cudaMalloc(&ctx->d_sched, sizeof(Sched)));
     if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
     CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
@@ -240,12 +242,15 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
-    cudaFree(ctx->d_lca_rep); cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->zero_start) cudaEventDestroy(ctx->zero_start);
+    if (ctx->zero_done) cudaEventDestroy(ctx->zero_done);
     delete ctx;
     return SLIMM_GPU_OK;
 }
@@ -383,20 +388,24 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     }
     {
         TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);   // the multisplit: slice starts + unit schedule, then group the items by slice
-        k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_sched, n_buckets, ctx->Bp, shift);
+        k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_sched, n_buckets);
         const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
         k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped);
         ctx->launches += 2;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);    // zero-fill fused in: every slice is created, filled and retired in L2
-        u64 units = n / ACC_TILE + n_buckets + 1;
-        for (u32 b = 0; b < n_buckets; ++b) {
-            const u64 lo = (u64)b << shift, hi = std::min<u64>(ctx->Bp, (u64)(b + 1) << shift);
-            units += (hi - lo + ZERO_TILE - 1) / ZERO_TILE;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));   // the histogram was zero-filled on the side stream meanwhile
+        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
+        {
+            // Measured on B200 (cfg5): the tighter the window of items in flight, the better the REDs hit L2 - 512 items
+            // per block 8.7 ms, 4096 12.0 ms, 65536 30.5 ms, grid-stride 28-34 ms.  SLIMM_ACC_SHAPE overrides (experiments).
+            static const char *shape = getenv("SLIMM_ACC_SHAPE");
+            const u32 per_block = shape && !strncmp(shape, "stride", 6) ? 0u : shape ? (u32)atoi(shape) : 512u;
+            const unsigned g = per_block ? (unsigned)std::max<u64>(1, ((u64)n + per_block - 1) / per_block)
+                                         : (unsigned)(ctx->sm_count * (shape && !strcmp(shape, "stride8") ? 8 : 16));
+            k_accumulate<<<g, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_sched, ctx->d_hist, per_block);
         }
-        k_accumulate_fused<<<(unsigned)units, 256, 0, ctx->stream>>>(ctx->d_sched, ctx->d_grouped, ctx->d_hist, ctx->Bp, shift, n_buckets);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -410,6 +419,7 @@ static void choose_scatter(slimm_gpu_ctx *ctx)
     // bucketed scatter when the interleaved histogram is much larger than L2 (and bin ids fit 31 bits)
     const bool big = ctx->Bp * 8 > (96ull << 20) && ctx->n >= (1u << 20);
     ctx->bucket_shift = BUCKET_SHIFT;
+    if (const char *e = getenv("SLIMM_BUCKET_SHIFT")) ctx->bucket_shift = (u32)std::max(16, std::min(28, atoi(e)));   // experiments
     while (((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift) > MAX_BUCKETS) ++ctx->bucket_shift;
     ctx->used_bucket = ctx->n > 0 && ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
 }
@@ -425,6 +435,14 @@ static int zero_state(slimm_gpu_ctx *ctx)
     TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
     choose_scatter(ctx);
     if (!ctx->used_bucket) CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
+    else {   // the big histogram is only needed by k_accumulate: zero-fill it on the side stream, under k_coverage / k_split
+        CU(cudaEventRecord(ctx->zero_start, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->zero_start, 0));
+        if (ctx->timing) { cudaEventRecord(ctx->ev[SLIMM_GPU_T_SORT][0], ctx->aux_stream); ctx->ev_used[SLIMM_GPU_T_SORT] = true; }   // debug: memset span
+        CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->aux_stream));
+        if (ctx->timing) cudaEventRecord(ctx->ev[SLIMM_GPU_T_SORT][1], ctx->aux_stream);
+        CU(cudaEventRecord(ctx->zero_done, ctx->aux_stream));
+    }
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
     return SLIMM_GPU_OK;
 }
@@ -562,7 +580,6 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     const u32 G = ctx->G;
     TimeScope ts(ctx, SLIMM_GPU_T_ASSIGN);
     CU(cudaMemsetAsync(ctx->d_assign, 0, ctx->assign_words * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_lca_rep, 0, (size_t)LCA_REPLICAS * 8 * G * 4, ctx->stream));
     u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     if (ctx->n) {
         const u32 n = (u32)ctx->n;
@@ -572,7 +589,7 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
         P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
         P.meta = ctx->d_meta; P.lin4 = (const uint4 *)ctx->d_lin; P.top_idx = ctx->d_top_idx; P.vb = ctx->d_valid_bits;
         P.G = G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv;
-        P.uniq2_extra = uniq2; P.lca_rep = ctx->d_lca_rep; P.child_mark = cm; P.fb_mark = fb; P.cov2 = ctx->d_cov2;
+        P.uniq2_extra = uniq2; P.lca_cnt = lca; P.child_mark = cm; P.fb_mark = fb; P.cov2 = ctx->d_cov2;
         P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.res_val = ctx->d_val;
         if (ctx->use_sorted) {
             k_assign<<<grid, 256, 0, ctx->stream>>>(RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted}, n, P);
@@ -581,8 +598,7 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
             k_assign<<<grid, 256, 0, ctx->stream>>>(RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos}, n, P);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, ctx->d_ref, 1, ctx->d_valid_bits, n);
         }
-        k_fold_lca<<<(8 * G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lca_rep, 8 * G, lca);
-        ctx->launches += 2 + (P.res_kind ? 1 : 0);
+        ctx->launches += 1 + (P.res_kind ? 1 : 0);
         CU(cudaGetLastError());
     }
     ctx->stage = ST_ASSIGN;
