@@ -212,6 +212,12 @@ int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa
 int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off, slimm_profile_row *rows,
                       uint64_t cap, uint64_t *n);
 
+/* 1 when the lineage table is tree-consistent (every taxon on one level with that rank in db.taxid__name, never 0,
+ * one parent): slimm_gpu_profile then runs the rank reduction on the device (k_rank_reduce); any other database
+ * takes the general host path, which replays the reference's set semantics ("profile tail"). */
+int slimm_profile_db_is_tree_consistent(uint32_t n_refs, const uint32_t *lineage, uint64_t n_taxa, const uint32_t *taxa_id,
+                                        const uint8_t *taxa_rank, const uint8_t *taxa_has_name, int *out);
+
 #ifdef __cplusplus
 }
 #endif

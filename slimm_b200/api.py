@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "slimm_gpu_get_lca_counts", "slimm_gpu_get_lca_children", "slimm_gpu_fetch_bins", "slimm_gpu_get_uniq2_nz",
     "slimm_gpu_read_results", "slimm_gpu_enable_timing", "slimm_gpu_get_timings", "slimm_gpu_get_launch_count",
     "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
+    "slimm_profile_db_is_tree_consistent",
 ]
 
 
@@ -113,6 +114,7 @@ def load_library():
     lib.slimm_gpu_set_scatter_mode.argtypes = [vp, C.c_int]
     lib.slimm_gpu_set_taxa.argtypes = [vp, u64, vp, vp, vp]
     lib.slimm_gpu_profile.argtypes = [vp, u32, C.c_float, C.POINTER(_Row), u64, C.POINTER(u64)]
+    lib.slimm_profile_db_is_tree_consistent.argtypes = [u32, vp, u64, vp, vp, vp, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -380,6 +382,19 @@ def profile_rows(ref_len, lineage, taxa: Dict[int, Tuple[int, str]], direct, chi
                  abundance_cut_off: float = 0.01, rank: int = 1) -> List[ProfileRow]:
     return profile_rows_arrays(ref_len, lineage, taxa_arrays(taxa), direct, children, uniq_reads_count2,
                                matches_count, avg_read_length, coverage_cut_off, abundance_cut_off, rank)
+
+
+def db_is_tree_consistent(lineage, taxa) -> bool:
+    """True when slimm_gpu_profile can run the rank reduction on the device for this database."""
+    lib = load_library()
+    lin = np.ascontiguousarray(lineage, dtype=np.uint32).reshape(-1, 8)
+    tid, trank, tname = taxa_arrays(taxa) if isinstance(taxa, dict) else taxa
+    out = C.c_int(0)
+    rc = lib.slimm_profile_db_is_tree_consistent(lin.shape[0], lin.ctypes.data, tid.size, tid.ctypes.data, trank.ctypes.data,
+                                                 tname.ctypes.data, C.byref(out))
+    if rc != 0:
+        raise SlimmGpuError(f"slimm_profile_db_is_tree_consistent: {lib.slimm_gpu_strerror(rc).decode()}")
+    return bool(out.value)
 
 
 class _DevicePointer:

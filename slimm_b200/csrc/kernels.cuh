@@ -1070,14 +1070,19 @@ k_assign(Rec rec, u32 n, AssignParams P)
                     const uint4 a0 = __ldg(P.lin4 + 2 * (u64)g0), b0 = __ldg(P.lin4 + 2 * (u64)g0 + 1);
                     mine = lineage_diff(P.lin4, g, a0, b0);
                 }
-                const u32 grp = win.M ? win.M : (1u << lane);      // REDUX over the lanes of my read
-                const u32 eq = ~__reduce_or_sync(grp, mine) & 0xFFu;
-                const bool fb = run_multi && eq == 0;
-                u32 owner = g0;
-                if (__any_sync(FULL, fb)) {                        // largest surviving reference id of the read
-                    const u32 top = __reduce_max_sync(grp, v ? g : 0u);
-                    if (fb) owner = top;
+                // OR of the difference masks over the lanes of my read: segmented suffix scan by shuffles, as many
+                // steps as the longest read of the window needs (REDUX with one mask per read serialises over the masks)
+                const int span = (int)__reduce_max_sync(FULL, run_multi ? (u32)(win.e - win.s) : 0u);
+                u32 acc = mine, gm = v ? g : 0u;
+                for (int dd = 1; dd <= span; dd <<= 1) {
+                    const u32 t = __shfl_down_sync(FULL, acc, dd), tg = __shfl_down_sync(FULL, gm, dd);
+                    if (win.whole && (int)lane + dd <= win.e) { acc |= t; gm = max(gm, tg); }
                 }
+                const int hd_lane = win.whole ? win.s : (int)lane;
+                const u32 eq = ~__shfl_sync(FULL, acc, hd_lane) & 0xFFu;
+                const bool fb = run_multi && eq == 0;
+                const u32 top = __shfl_sync(FULL, gm, hd_lane);           // largest surviving reference id of the read
+                const u32 owner = fb ? top : g0;
                 const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1);
                 if (v && run_multi) mark_child(P, g, fb, level, owner);
                 const bool is_lca = is_head && run_multi;
@@ -1105,6 +1110,58 @@ __global__ void k_read_results_unique(unsigned char *__restrict__ res_kind, u32 
     if (i >= n || res_kind[i] != 3) return;
     const u32 g = ref[(u64)i * ref_stride];
     if (is_valid(vb, g)) { res_kind[i] = 1; res_val[i] = g; } else res_kind[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: per-rank segmented reduction of read counts and contributing-reference sets, for databases whose
+// lineage table is tree-consistent (every taxon sits on one level, carries that rank in db.taxid__name, and
+// all references under it share the levels above; no zero slots).  There phases 2 and 3 of
+// get_reads_lca_count (src/slimm.hpp:560-610) reduce to sums over the references below a taxon:
+//   count[t on level L]    = sum over g under t of ( uniq_reads_count2[g] + sum_{l <= L} lca_count[g][l] )
+//   children[t on level L] = { g under t : g carries a child mark on a level <= L, or uniq_reads_count2[g] > 0 }
+//                            (+ the fallback marks of level-7 taxa)
+// and write_abundance (:733-843) needs count, |children|, sum of their lengths, min and max per taxon of the
+// requested rank and its parent rank.  One thread per reference; taxa are addressed by a per-level dense
+// index (lvl_idx[L][g]).  Any other database takes the general host path (profile_host.cpp).
+// agg layout: [which 0: rank, 1: parent rank][count | kn | klen | kmin | kmax][G]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rank_reduce(const u32 *__restrict__ assign /* uniq2[G] | lca[G*8] | child_mark[G*8] | fb_mark[n_top*G] */, const uint4 *__restrict__ meta,
+              const u32 *__restrict__ lvl_idx /*[8][G]*/, const u32 *__restrict__ top_lvl7 /*[n_top] level-7 index of fallback row*/,
+              u32 G, u32 n_top, u32 rk, u32 *__restrict__ agg)
+{
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const u32 u2 = assign[g];
+    const u32 *lc = assign + G + (u64)g * 8, *cm = assign + (u64)9 * G + (u64)g * 8;   // G need not be a multiple of 4: scalar loads
+    u32 c[8], marks = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) { c[l] = lc[l]; marks |= (u32)(cm[l] != 0) << l; }
+    const u32 len = meta[g].x;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const u32 L = rk + which;
+        u32 cnt = u2;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) if ((u32)l <= L) cnt += c[l];
+        const u32 t = __ldg(lvl_idx + (u64)L * G + g);
+        u32 *a = agg + (u64)which * 5 * G;
+        if (cnt) atomicAdd(a + t, cnt);
+        if ((marks & ((2u << L) - 1u)) != 0 || u2 > 0) {
+            atomicAdd(a + G + t, 1u);
+            atomicAdd(a + 2 * (u64)G + t, len);
+            atomicMin(a + 3 * (u64)G + t, g);
+            atomicMax(a + 4 * (u64)G + t, g);
+        }
+    }
+    if (rk + 1 == 7)                                               // children of a fallback LCA may lie outside its subtree
+        for (u32 r = 0; r < n_top; ++r)
+            if (assign[(u64)17 * G + (u64)r * G + g]) {
+                u32 *a = agg + (u64)5 * G;
+                const u32 t = top_lvl7[r];
+                atomicAdd(a + G + t, 1u);
+                atomicMin(a + 3 * (u64)G + t, g);
+            }
 }
 
 // uniq_reads_count2[g] = (valid[g] ? uniq_reads_count[g] : 0) + reads that became unique;

@@ -43,6 +43,7 @@ ProfilePlan::ProfilePlan(u32 n_refs, const u32 *ref_len, const u32 *lineage, u64
     kids.resize(T);
     pab.assign(T, 0.0f); sab.assign(T, 0.0f); pcnt.assign(T, 0); scnt.assign(T, 0); has_p.assign(T, 0); has_s.assign(T, 0);
     stamp.assign(G, 0); kmin.assign(T, 0xFFFFFFFFu); kmax.assign(T, 0);
+    check_consistency();
 }
 
 int ProfilePlan::find(u32 taxon) const
@@ -192,6 +193,93 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
     return SLIMM_GPU_OK;
 }
 
+// A lineage table is tree-consistent when every taxon occupies one level only, db.taxid__name gives it exactly
+// that level as its rank, it is never 0, and all references that share it share every level above it.  Then the
+// aggregation of slimm::get_reads_lca_count / write_abundance does not depend on visit order or on which child is
+// "first", and reduces to sums over the references below a taxon (k_rank_reduce).
+void ProfilePlan::check_consistency()
+{
+    consistent = false;
+    const size_t T = vals.size();
+    std::vector<u32> level_of(T, 0xFFFFFFFFu), parent_of(T, 0xFFFFFFFFu);
+    for (u32 g = 0; g < G; ++g)
+        for (u32 l = 0; l < 8; ++l) {
+            const u32 t = slot_t[(size_t)g * 8 + l];
+            if (vals[t] == 0 || rank[t] != l) return;
+            if (level_of[t] == 0xFFFFFFFFu) level_of[t] = l;
+            else if (level_of[t] != l) return;
+            if (l < 7) {
+                const u32 up = slot_t[(size_t)g * 8 + l + 1];
+                if (parent_of[t] == 0xFFFFFFFFu) parent_of[t] = up;
+                else if (parent_of[t] != up) return;
+            }
+        }
+    lvl_idx.assign((size_t)8 * G, 0);
+    std::vector<u32> pos(T, 0);
+    for (u32 l = 0; l < 8; ++l) lvl_taxa[l].clear();
+    for (size_t t = 0; t < T; ++t)
+        if (level_of[t] != 0xFFFFFFFFu) { pos[t] = (u32)lvl_taxa[level_of[t]].size(); lvl_taxa[level_of[t]].push_back((u32)t); }
+    for (u32 g = 0; g < G; ++g)
+        for (u32 l = 0; l < 8; ++l) lvl_idx[(size_t)l * G + g] = pos[slot_t[(size_t)g * 8 + l]];
+    consistent = true;
+}
+
+int ProfilePlan::finish_from_aggregates(const u32 *agg, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
+                                        float abundance_cut_off, u32 rk, std::vector<slimm_profile_row> &out) const
+{
+    out.clear();
+    if (!consistent || rk < 1 || rk > 6) return SLIMM_GPU_EINVAL;
+    const u32 pr = rk + 1;
+    const u32 *cnt_r = agg, *kn_r = agg + G, *klen_r = agg + 2 * (size_t)G, *kmin_r = agg + 3 * (size_t)G, *kmax_r = agg + 4 * (size_t)G;
+    const u32 *cnt_p = agg + 5 * (size_t)G, *kn_p = cnt_p + G, *kmin_p = cnt_p + 3 * (size_t)G;
+    const float R = (float)matches_count;
+    const std::vector<u32> &tr = lvl_taxa[rk], &tp = lvl_taxa[pr];
+    std::vector<float> sab_l(tp.size(), 0.0f);
+    std::vector<u32> scnt_l(tp.size(), 0);
+    std::vector<uint8_t> has_s_l(tp.size(), 0);
+    float sum_ab = 0.0f;
+    u32 sum_cnt = 0;
+    for (size_t j = 0; j < tr.size(); ++j) {                      // write_abundance rank pass (:776-813), ascending taxon
+        const u32 c = cnt_r[j];
+        if (c == 0) continue;
+        if (kn_r[j] == 0) return SLIMM_GPU_EINVAL;
+        const u32 t = tr[j];
+        const u32 gl = klen_r[j] / kn_r[j];                        // u32 sum (wraps) / count (:785-789)
+        const float cov = (float)(u32)(c * avg_read_length) / gl;  // u32 product (:792)
+        const float ab = (float)c / R * 100;
+        const u32 p = lvl_idx[(size_t)pr * G + kmax_r[j]];         // parent of the last child iterated (std::set order)
+        if (!has_s_l[p]) { has_s_l[p] = 1; sab_l[p] = ab; scnt_l[p] = c; }
+        else { sab_l[p] += ab; scnt_l[p] += c; }
+        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) continue;
+        slimm_profile_row r;
+        r.taxon = vals[t]; r.kind = 0; r.read_count = c; r.first_child = kmin_r[j]; r.abundance = ab;
+        out.push_back(r);
+        sum_ab += ab;
+        sum_cnt += c;
+    }
+    for (size_t j = 0; j < tp.size(); ++j) {                      // "<parent>*" rows (:816-831), ascending taxon
+        if (!has_s_l[j]) continue;
+        const u32 p = tp[j];
+        const bool has_p = cnt_p[j] != 0;
+        const float uab = (has_p ? (float)cnt_p[j] / R * 100 : 0.0f) - sab_l[j];
+        const u32 ucnt = (has_p ? cnt_p[j] : 0u) - scnt_l[j];
+        if (uab > abundance_cut_off && named[p]) {
+            slimm_profile_row r;
+            r.taxon = vals[p]; r.kind = 1; r.read_count = ucnt; r.abundance = uab;
+            r.first_child = kn_p[j] ? kmin_p[j] : 0xFFFFFFFFu;
+            out.push_back(r);
+            sum_cnt += ucnt;
+            sum_ab += uab;
+        }
+    }
+    slimm_profile_row last;
+    last.taxon = 0; last.kind = 2; last.first_child = 0xFFFFFFFFu;
+    last.abundance = 100.0 - sum_ab;                               // double minus float (:835)
+    last.read_count = matches_count - sum_cnt;                     // u32 wrap
+    out.push_back(last);
+    return SLIMM_GPU_OK;
+}
+
 }  // namespace slimm_host
 
 extern "C" int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_row *rows, uint64_t cap, uint64_t *n_out)
@@ -216,5 +304,15 @@ extern "C" int slimm_profile_rows(const slimm_profile_input *in, slimm_profile_r
     *n_out = out.size();
     for (uint64_t i = 0; i < out.size() && i < cap; ++i)
         if (rows) rows[i] = out[i];
+    return SLIMM_GPU_OK;
+}
+
+extern "C" int slimm_profile_db_is_tree_consistent(uint32_t n_refs, const uint32_t *lineage, uint64_t n_taxa, const uint32_t *taxa_id,
+                                                   const uint8_t *taxa_rank, const uint8_t *taxa_has_name, int *out)
+{
+    if (!lineage || !out || (n_taxa && (!taxa_id || !taxa_rank || !taxa_has_name))) return SLIMM_GPU_EINVAL;
+    std::vector<uint32_t> len(n_refs, 1);
+    slimm_host::ProfilePlan plan(n_refs, len.data(), lineage, n_taxa, taxa_id, taxa_rank, taxa_has_name);
+    *out = plan.consistent ? 1 : 0;
     return SLIMM_GPU_OK;
 }

@@ -26,6 +26,10 @@ struct ProfilePlan {
     std::vector<u32> touched, snapshot;
     std::vector<u32> stamp, kmin, kmax;   // duplicate filter over references; smallest / largest member of a normalized set
     u32 epoch = 0;
+    // tree-consistent databases: per-level dense taxon index of every reference and the taxa of each level (ascending)
+    bool consistent = false;
+    std::vector<u32> lvl_idx;            // [8][G]
+    std::vector<u32> lvl_taxa[8];        // dense taxon ids (indices into vals) of the level, ascending
 
     ProfilePlan(u32 n_refs, const u32 *ref_len, const u32 *lineage, u64 n_taxa, const u32 *taxa_id,
                 const uint8_t *taxa_rank, const uint8_t *taxa_has_name);
@@ -36,7 +40,12 @@ struct ProfilePlan {
     int finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
                float abundance_cut_off, u32 rank, std::vector<slimm_profile_row> &out);
 
+    // rows from the per-level aggregates of k_rank_reduce (agg: [2][count|kn|klen|kmin|kmax][G]); consistent databases only
+    int finish_from_aggregates(const u32 *agg, u32 matches_count, u32 avg_read_length, float coverage_cut_off,
+                               float abundance_cut_off, u32 rank, std::vector<slimm_profile_row> &out) const;
+
 private:
+    void check_consistency();
     void touch(u32 t);
     void normalize(u32 t);
 };

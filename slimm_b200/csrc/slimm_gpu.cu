@@ -69,6 +69,9 @@ struct slimm_gpu_ctx {
     bool ev_used[SLIMM_GPU_T_COUNT] = {};
     u64 launches = 0;
     float tail_host_ms = 0.0f;
+    // rank reduction on the device (tree-consistent databases)
+    u32 *d_lvl_idx = nullptr, *d_top_lvl7 = nullptr, *d_agg = nullptr; u32 *h_agg = nullptr; DevScalars *h_sc = nullptr;
+    int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
     std::vector<u32> h_assign;              // host copy of the assign block
     bool h_assign_ok = false;
     std::string err;
@@ -211,6 +214,7 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_valid_bytes, G));
     CU(cudaMalloc(&ctx->d_assign, ctx->assign_words * 4));
     CU(cudaMalloc(&ctx->d_sched, sizeof(Sched)));
+    if (const char *e = getenv("SLIMM_GPU_TAIL")) ctx->tail_mode = !strcmp(e, "host") ? 1 : -1;
     if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
     CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
     if (const char *e = getenv("SLIMM_GPU_SCATTER")) ctx->scatter_mode = !strcmp(e, "direct") ? 0 : !strcmp(e, "bucket") ? 1 : -1;
@@ -242,7 +246,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
-    cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
+    cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -340,7 +344,8 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
     const u32 n = (u32)ctx->n;
     const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
-    const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 6));
+    static const int cov_ctas = getenv("SLIMM_COV_CTAS") ? atoi(getenv("SLIMM_COV_CTAS")) : 6;   // CTAs per SM (experiments)
+    const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * cov_ctas));
     // compact stream of the multi-mapped reads (k_assign's input), one slot per chunk
     const bool want_idx = (ctx->flags & (SLIMM_GPU_KEEP_UNIQ_COV2 | SLIMM_GPU_READ_RESULTS)) != 0;
     if (ctx->cw_chunks < n_chunks) {
@@ -810,6 +815,21 @@ int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa
 {
     if (!ctx || (n_taxa && (!taxa_id || !taxa_rank || !taxa_has_name))) return SLIMM_GPU_EINVAL;
     ctx->plan.reset(new slimm_host::ProfilePlan(ctx->G, ctx->h_len.data(), ctx->h_lin.data(), n_taxa, taxa_id, taxa_rank, taxa_has_name));
+    if (ctx->plan->consistent) {             // the rank reduction can run on the device (k_rank_reduce)
+        CU(cudaSetDevice(ctx->device));
+        const u32 G = ctx->G;
+        if (!ctx->d_lvl_idx) {
+            CU(cudaMalloc(&ctx->d_lvl_idx, (size_t)8 * G * 4));
+            CU(cudaMalloc(&ctx->d_top_lvl7, (size_t)std::max<u32>(ctx->n_top, 1) * 4));
+            CU(cudaMalloc(&ctx->d_agg, (size_t)10 * G * 4));
+            CU(cudaHostAlloc((void **)&ctx->h_agg, (size_t)10 * G * 4, cudaHostAllocDefault));
+            CU(cudaHostAlloc((void **)&ctx->h_sc, sizeof(DevScalars), cudaHostAllocDefault));
+        }
+        std::vector<u32> top7(std::max<u32>(ctx->n_top, 1), 0);
+        for (u32 g = 0; g < G; ++g) top7[ctx->h_top_idx[g]] = ctx->plan->lvl_idx[(size_t)7 * G + g];
+        CU(cudaMemcpy(ctx->d_lvl_idx, ctx->plan->lvl_idx.data(), (size_t)8 * G * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_top_lvl7, top7.data(), top7.size() * 4, cudaMemcpyHostToDevice));
+    }
     return SLIMM_GPU_OK;
 }
 
@@ -817,6 +837,32 @@ int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off
 {
     if (!ctx || !n) return SLIMM_GPU_EINVAL;
     if (!ctx->plan) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_set_taxa has not been called");
+    if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
+    if (rank < 1 || rank > 6) return fail(ctx, SLIMM_GPU_EINVAL, "rank must be 1 (species) .. 6 (phylum)");
+    if (ctx->plan->consistent && ctx->tail_mode != 1) {
+        // K7: per-rank segmented reduction on the device, only the per-taxon aggregates of two ranks come back
+        CU(cudaSetDevice(ctx->device));
+        { int rc0 = finish_assign(ctx); if (rc0) return rc0; }
+        const u32 G = ctx->G;
+        CU(cudaMemsetAsync(ctx->d_agg, 0, (size_t)10 * G * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_agg + (size_t)3 * G, 0xFF, (size_t)G * 4, ctx->stream));   // kmin of the rank
+        CU(cudaMemsetAsync(ctx->d_agg + (size_t)8 * G, 0xFF, (size_t)G * 4, ctx->stream));   // kmin of the parent rank
+        k_rank_reduce<<<(G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_assign, ctx->d_meta, ctx->d_lvl_idx, ctx->d_top_lvl7, G, ctx->n_top, rank, ctx->d_agg);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ctx->h_agg, ctx->d_agg, (size_t)10 * G * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<slimm_profile_row> out;
+        int rc0 = ctx->plan->finish_from_aggregates(ctx->h_agg, (u32)ctx->h_sc->n_reads, ctx->avg, ctx->h_sc->cut, abundance_cut_off, rank, out);
+        if (rc0) return fail(ctx, rc0, "profile aggregation failed (inconsistent stage outputs)");
+        *n = out.size();
+        for (u64 i = 0; i < out.size() && i < cap; ++i)
+            if (rows) rows[i] = out[i];
+        ctx->tail_host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return SLIMM_GPU_OK;
+    }
     int rc = fetch_assign(ctx);
     if (rc) return rc;
     slimm_gpu_summary sm;

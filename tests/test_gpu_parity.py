@@ -188,3 +188,30 @@ def test_bucketed_scatter_many_buckets():
                 np.testing.assert_array_equal(st.uniq_reads_count2, res.uniq_reads_count2)
                 np.testing.assert_array_equal(st.nz_bins, res.nz)
                 assert gpu.lca_counts() == res.direct
+
+
+@pytest.mark.parametrize("env,value", [("SLIMM_GPU_TAIL", "host"), ("SLIMM_GPU_CUTOFF", "global")])
+def test_alternative_paths_agree(env, value, monkeypatch):
+    """The general host tail / the global-memory cut-off sort give the same rows and statistics as the default
+    device rank reduction / cluster sort."""
+    contigs, rec, lineage = _synthetic(2000, 600_000, 99, multi_frac=0.35)
+    tax, accs = synth.make_taxonomy(2000)
+    db = synth.database_for(tax)
+    taxa = {t: v for t, v in db.taxid__name.items()}
+    assert api.db_is_tree_consistent(lineage, taxa)
+    res = oracle.run(contigs.lengths, lineage, 1000, 100, 0.9, rec.read_id, rec.ref_id, rec.begin_pos)
+    out = []
+    for use_alt in (False, True):
+        if use_alt:
+            monkeypatch.setenv(env, value)
+        with api.SlimmGpu(contigs.lengths, lineage, 1000, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
+            gpu.set_taxa(taxa)
+            gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
+            gpu.run(0.9)
+            compare_with_oracle(gpu, res, lineage, check_bins=False)
+            for rank in (1, 2, 6):
+                out.append([(r.taxon, r.kind, r.read_count, r.first_child, np.float64(r.abundance).tobytes())
+                            for r in gpu.profile(rank, 0.001)])
+    half = len(out) // 2
+    assert out[:half] == out[half:]
+    assert len(out[0]) > 10

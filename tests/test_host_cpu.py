@@ -44,3 +44,26 @@ def test_profile_rows_host_tail(case_name, run_name):
                             res.n_reads, case.avg_read_length, float(res.cut), run.abundance_cut_off, run.rank)
     lines = report.profile_lines(rows, case.lineage, case.name_of, run.rank)
     assert_profiles_match(os.path.join(run.path, "profile.tsv"), lines)
+
+
+def test_tree_consistency_classification():
+    """The device rank reduction is only taken for tree-consistent databases; fixtures with contigs missing from
+    the database (all-zero lineages) must fall back to the general host path."""
+    expected = {"synth1k": True, "lca64": True, "missing": False, "quirk": False}
+    for name, want in expected.items():
+        case = load_case(name)
+        taxa = {t: (case.rank_of[t], case.name_of[t]) for t in case.rank_of}
+        assert api.db_is_tree_consistent(case.lineage, taxa) == want, name
+    # a taxon that appears on two levels, or under two parents, is not consistent
+    lin = np.array([[11, 1, 2, 3, 4, 5, 6, 7], [12, 1, 2, 3, 4, 5, 6, 7]], dtype=np.uint32)
+    taxa = {t: (r, "n") for r, t in enumerate([0, 1, 2, 3, 4, 5, 6, 7])}
+    taxa.update({11: (0, "a"), 12: (0, "b")})
+    del taxa[0]
+    assert api.db_is_tree_consistent(lin, taxa)
+    bad = lin.copy(); bad[1, 2] = 9
+    taxa2 = dict(taxa); taxa2[9] = (2, "x")
+    assert not api.db_is_tree_consistent(bad, taxa2)          # species 1 under two genera
+    bad = lin.copy(); bad[1, 3] = 2
+    assert not api.db_is_tree_consistent(bad, taxa)           # taxon 2 on two levels
+    taxa3 = dict(taxa); taxa3[5] = (6, "wrong rank")
+    assert not api.db_is_tree_consistent(lin, taxa3)
