@@ -9,8 +9,8 @@ path over the workload's records:
   * `value`  : records already resident in HBM when the timed region starts (slimm_gpu_push_device),
   * `e2e`    : the same pass through the C ABI with HOST (pinned) buffers, H2D copies of the three
                record arrays and D2H of the results inside the timed region,
-  * `roofline`: the coverage kernel (dominant), algorithmic bytes / its CUDA-event duration / measured
-               HBM peak (MEASURED_PEAKS.json),
+  * `roofline`: the kernel with the largest share of the step; its algorithmic bytes /
+               its CUDA-event duration / measured HBM peak (MEASURED_PEAKS.json),
   * `cpu_baseline`: the unmodified reference binary (oracle/_ref/slimm) on a bounded sample, 1 core.
 `--impl reference` times that reference binary as its own arm.
 """
@@ -255,21 +255,20 @@ def main():
     gpu.set_taxa(taxa_arrays)
     flush = None if wl["N"] * 12 > 400e6 else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
-    def allreduce_ptr(ptr, n_words, dtype=torch.int32):
-        t = api.device_tensor(ptr, n_words, dtype, dev)
-        dist.all_reduce(t)
+    if world > 1:
+        from slimm_b200 import dist as sdist
 
     def hot_path():
-        """coverage -> (NCCL sum of the bin histograms) -> filter -> assign -> (NCCL sum) -> profile"""
-        gpu.coverage()
+        """coverage -> filter -> assign -> profile; with several GPUs the items are routed to the rank that owns their
+        histogram slice (one NCCL all-to-all, 4 B/record) and only per-reference statistics and the assign block are
+        summed over ranks (slimm_b200/dist.py)."""
         if world > 1:
-            p, n = gpu.bins_device(); allreduce_ptr(p, n)
-            p, n = gpu.counters_device(); allreduce_ptr(p, n, torch.int64)
-            gpu.set_global_hits(wl["N"])
-        gpu.filter(wl["cc"], 0)
-        gpu.assign()
-        if world > 1:
-            p, n = gpu.assign_device(); allreduce_ptr(p, n)
+            gpu.set_shard(rank, world)
+            sdist.run_sharded(gpu, dev, wl["cc"], 0, wl["N"])
+        else:
+            gpu.coverage()
+            gpu.filter(wl["cc"], 0)
+            gpu.assign()
         return profile_tail(api, gpu, contigs, lineage, taxa_arrays, wl["cc"])
 
     def step_resident():
@@ -312,23 +311,32 @@ def main():
     ms_per_step = total_ms / args.steps
     value = wl["N"] / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (coverage): 16 B of SoA per record + one 8 B read-modify-write per
-    # distinct (read, ref) pair + 8 B more per unique read (split per kernel in DESIGN.md)
+    # roofline: algorithmic bytes per kernel as in DESIGN.md section 3 (N*(16+16) + P*8 + U*8 + 16*B),
+    # for this rank's share; the kernel with the largest share of the step is the one reported
     peak, peak_src = measured_peak_gbs()
-    P, U, B = summ.n_pairs, summ.uniq_matches_count, summ.n_bins
-    if world > 1:   # this rank's share of the pairs / unique reads
-        P, U = P / world, U / world
+    P, U, B = summ.n_pairs / world, summ.uniq_matches_count / world, summ.n_bins / world
     kernel_ms = {k: statistics.mean(t[k] for t in ktimes) for k in ktimes[0]}
-    # coverage = bucket count + emit + accumulate when the bucketed scatter is used, one kernel otherwise
-    cov_ms = kernel_ms["bucket_count"] + kernel_ms["coverage"] + kernel_ms["accumulate"]
-    cov_bytes = 16.0 * n_local + 8.0 * P + 8.0 * U
-    achieved = cov_bytes / (cov_ms * 1e-3) / 1e9
+    bucketed = kernel_ms["accumulate"] > 0
+    alg = {"coverage": 16.0 * n_local + (0.0 if bucketed else 8.0 * P + 8.0 * U + 8.0 * B),
+           "accumulate": 8.0 * P + 8.0 * U + 8.0 * B, "stats": 8.0 * B, "assign": 16.0 * n_local}
+    names = {"coverage": "k_coverage", "accumulate": "k_accumulate (+ histogram memset on the side stream)",
+             "stats": "k_ref_stats", "assign": "k_assign"}
+    dom = max((k for k in alg if kernel_ms.get(k, 0) > 0), key=lambda k: kernel_ms[k])
+    traffic = None
+    try:   # DRAM bytes per record of each kernel from the committed ncu capture (profiles/), scaled to this launch
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload in tr and dom in tr[args.workload]:
+            traffic = tr[args.workload][dom]["dram_bytes_per_record"] * n_local
+    except Exception:
+        pass
     pipe_bytes = 32.0 * n_local + 8.0 * P + 8.0 * U + 16.0 * B
-    roofline = {"bound": "hbm", "kernel": "coverage scatter (k_bucket_count + k_coverage + k_accumulate)"
-                if kernel_ms["accumulate"] > 0 else "k_coverage", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": cov_bytes, "kernel_ms": cov_ms,
-                "pipeline": {"algorithmic_bytes_per_step": pipe_bytes, "ms_per_step": ms_per_step,
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kernel_ms[dom],
+                "per_kernel": {k: {"ms": kernel_ms[k], "algorithmic_bytes": alg[k],
+                                   "frac": (alg[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak) if kernel_ms[k] > 0 else None}
+                               for k in alg},
+                "pipeline": {"algorithmic_bytes_per_step": pipe_bytes * world, "ms_per_step": ms_per_step,
                              "achieved": pipe_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac": pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "kernel_ms": kernel_ms}}
 
@@ -349,7 +357,7 @@ def main():
 
         e_total_ms, _, _ = timed(step_e2e, 1, max(1, min(args.steps, 3)))
         e_steps = max(1, min(args.steps, 3))
-        d2h = (17 + 8) * wl["G"] * 4 + wl["G"] * 25 + 96
+        d2h = 10 * wl["G"] * 4 + 96   # per-taxon aggregates of two ranks + scalars (slimm_gpu_profile)
         e2e = {"value": wl["N"] / (e_total_ms / e_steps * 1e-3), "unit": "records/s",
                "h2d_bytes_per_step": 12 * h[0].numel(), "d2h_bytes_per_step": d2h, "steps": e_steps,
                "note": "slimm_gpu_push from pinned host SoA (3 x u32 per record) + all stages + result readback"}

@@ -120,6 +120,25 @@ int slimm_gpu_counters_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u64)
 /* Tell the context the global number of kept records when records are sharded over ranks. */
 int slimm_gpu_set_global_hits(slimm_gpu_ctx *ctx, uint64_t hits);
 
+/* ---- several GPUs, one process each: histogram slices sharded over ranks ------------------------------------------
+ * Reads are sharded by read id (the caller pushes each rank its reads); the bins are sharded by histogram slice
+ * (2^22 consecutive padded bins): rank r of n owns slices [S*r/n, S*(r+1)/n).  In a sharded run slimm_gpu_coverage
+ * stops after grouping this rank's items by slice; the caller routes every item to the rank that owns its slice
+ * (one all-to-all of 4 bytes per record; the per-slice counts give the split sizes), hands the received items to
+ * slimm_gpu_accumulate_items, which fills and scans only the owned bins, and sums the partial per-reference
+ * statistics (slimm_gpu_stats_device, 16 bytes per reference) and the read counters (slimm_gpu_counters_device)
+ * over ranks before slimm_gpu_filter.  Nothing of the size of the histogram ever crosses NVLink.
+ * uniq_cov2 bins (SLIMM_GPU_KEEP_UNIQ_COV2) are a single-GPU feature. */
+int slimm_gpu_set_shard(slimm_gpu_ctx *ctx, uint32_t rank, uint32_t n_ranks);
+/* items per slice of this rank after slimm_gpu_coverage (host copy; counts may be NULL to query n_slices) */
+int slimm_gpu_get_slice_counts(slimm_gpu_ctx *ctx, uint32_t *counts, uint32_t cap, uint32_t *n_slices);
+/* device pointer to this rank's items grouped by slice (u32 each, slice s starts at the sum of the counts before it) */
+int slimm_gpu_items_device(slimm_gpu_ctx *ctx, void **d_items);
+/* apply the items received for the owned slices (device pointer) and scan the owned bins */
+int slimm_gpu_accumulate_items(slimm_gpu_ctx *ctx, const uint32_t *d_items, uint64_t n_items);
+/* device pointer to {nz, reads_count, uniq nz, uniq_reads_count}[n_refs] (u32) for the sum over ranks */
+int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
+
 /* Stage 2 - reference filter.  Replaces none_zero_bin_count / cov_percent / uniq_cov_percent
  * (src/reference_contig.hpp:84-91,148-155), coverage_cut_off / uniq_coverage_cut_off
  * (src/slimm.hpp:328-344,672-688) with get_quantile_cut_off (src/misc.hpp:197-216) and the
@@ -159,10 +178,11 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
                            uint64_t cap, uint64_t *n);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
-enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_BCOUNT, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_ACCUM,
+enum { SLIMM_GPU_T_SORT = 0, SLIMM_GPU_T_ZERO, SLIMM_GPU_T_SPLIT, SLIMM_GPU_T_COVERAGE, SLIMM_GPU_T_ACCUM,
        SLIMM_GPU_T_STATS, SLIMM_GPU_T_CUTOFF, SLIMM_GPU_T_ASSIGN, SLIMM_GPU_T_TAIL_HOST, SLIMM_GPU_T_COUNT };
 int slimm_gpu_enable_timing(slimm_gpu_ctx *ctx, int on);
-/* CUDA-event durations (ms) of the last run, per kernel group (SLIMM_GPU_T_TAIL_HOST: host wall time of the rank
+/* CUDA-event durations (ms) of the last run, per kernel group (SLIMM_GPU_T_ZERO: the histogram memset, which runs on a
+ * second stream underneath k_coverage / k_split when the bucketed scatter is used; SLIMM_GPU_T_TAIL_HOST: host wall time of the rank
  * aggregation in slimm_gpu_profile, after the results arrived), and launches issued since create */
 int slimm_gpu_get_timings(slimm_gpu_ctx *ctx, float *ms, int n);
 int slimm_gpu_get_launch_count(slimm_gpu_ctx *ctx, uint64_t *n);

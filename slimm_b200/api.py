@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libslimm_gpu.so")
 
 KEEP_UNIQ_COV2 = 1
 READ_RESULTS = 2
-TIMING_NAMES = ["sort", "zero", "bucket_count", "coverage", "accumulate", "stats", "cutoff", "assign", "tail_host"]
+TIMING_NAMES = ["sort", "zero", "split", "coverage", "accumulate", "stats", "cutoff", "assign", "tail_host"]
 
 EXPORTED_SYMBOLS = [
     "slimm_gpu_strerror", "slimm_gpu_last_error", "slimm_gpu_device_count", "slimm_gpu_create", "slimm_gpu_destroy",
@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "slimm_gpu_get_lca_counts", "slimm_gpu_get_lca_children", "slimm_gpu_fetch_bins", "slimm_gpu_get_uniq2_nz",
     "slimm_gpu_read_results", "slimm_gpu_enable_timing", "slimm_gpu_get_timings", "slimm_gpu_get_launch_count",
     "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
-    "slimm_profile_db_is_tree_consistent",
+    "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
+    "slimm_gpu_accumulate_items", "slimm_gpu_stats_device",
 ]
 
 
@@ -114,6 +115,11 @@ def load_library():
     lib.slimm_gpu_set_scatter_mode.argtypes = [vp, C.c_int]
     lib.slimm_gpu_set_taxa.argtypes = [vp, u64, vp, vp, vp]
     lib.slimm_gpu_profile.argtypes = [vp, u32, C.c_float, C.POINTER(_Row), u64, C.POINTER(u64)]
+    lib.slimm_gpu_set_shard.argtypes = [vp, u32, u32]
+    lib.slimm_gpu_get_slice_counts.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    lib.slimm_gpu_items_device.argtypes = [vp, C.POINTER(vp)]
+    lib.slimm_gpu_accumulate_items.argtypes = [vp, vp, u64]
+    lib.slimm_gpu_stats_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     lib.slimm_profile_db_is_tree_consistent.argtypes = [u32, vp, u64, vp, vp, vp, C.POINTER(C.c_int)]
     _lib = lib
     return lib
@@ -234,6 +240,30 @@ class SlimmGpu:
     def assign_device(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_uint64()
         self._check(self._lib.slimm_gpu_assign_device(self._ctx, C.byref(p), C.byref(n)), "assign_device")
+        return p.value, n.value
+
+    # -- sharded runs (several GPUs) -----------------------------------------------------------
+    def set_shard(self, rank: int, n_ranks: int):
+        self._check(self._lib.slimm_gpu_set_shard(self._ctx, rank, n_ranks), "set_shard")
+
+    def slice_counts(self) -> np.ndarray:
+        n = C.c_uint32()
+        self._check(self._lib.slimm_gpu_get_slice_counts(self._ctx, None, 0, C.byref(n)), "get_slice_counts")
+        counts = np.zeros(n.value, dtype=np.uint32)
+        self._check(self._lib.slimm_gpu_get_slice_counts(self._ctx, counts.ctypes.data, n.value, C.byref(n)), "get_slice_counts")
+        return counts
+
+    def items_device(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.slimm_gpu_items_device(self._ctx, C.byref(p)), "items_device")
+        return p.value or 0
+
+    def accumulate_items(self, items_ptr: int, n_items: int):
+        self._check(self._lib.slimm_gpu_accumulate_items(self._ctx, C.c_void_p(items_ptr), n_items), "accumulate_items")
+
+    def stats_device(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.slimm_gpu_stats_device(self._ctx, C.byref(p), C.byref(n)), "stats_device")
         return p.value, n.value
 
     def set_global_hits(self, hits: int):

@@ -452,9 +452,10 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
 // behind a memset, and the memset overlaps k_coverage / k_split on a second stream for free.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsigned long long *__restrict__ hist, u32 per_block)
+k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsigned long long *__restrict__ hist, u32 per_block,
+             u32 n_given /* used when sd == nullptr: items received from other ranks */)
 {
-    const u32 n_items = sd->total_items;
+    const u32 n_items = sd ? sd->total_items : n_given;
     if (per_block == 0) {                                          // grid-stride
         const u32 stride = gridDim.x * blockDim.x;
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items && i + stride > i; i += stride) {
@@ -481,14 +482,14 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 // ------------------------------------------------------------------------------------------------
 #define STATS_STEPS_PER_WARP 16
 __global__ void __launch_bounds__(256)
-k_ref_stats(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict__ off /*[G+1] padded, in bins*/,
+k_ref_stats(const uint4 *__restrict__ hist4, u64 step_lo, u64 n_steps /* end of the step range */, const u64 *__restrict__ off /*[G+1] padded, in bins*/,
             u32 G, u32 *__restrict__ stats)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 chunk = warp; chunk * STATS_STEPS_PER_WARP < n_steps; chunk += n_warps) {
-        const u64 s0 = chunk * STATS_STEPS_PER_WARP;
+    for (u64 chunk = warp; step_lo + chunk * STATS_STEPS_PER_WARP < n_steps; chunk += n_warps) {
+        const u64 s0 = step_lo + chunk * STATS_STEPS_PER_WARP;
         const u64 s1 = min(s0 + (u64)STATS_STEPS_PER_WARP, n_steps);
         u32 lo = 0, hi = G;                              // largest g with off[g] <= first bin of the chunk
         const u64 bin0 = s0 * 64;

@@ -71,6 +71,8 @@ struct slimm_gpu_ctx {
     float tail_host_ms = 0.0f;
     // rank reduction on the device (tree-consistent databases)
     u32 *d_lvl_idx = nullptr, *d_top_lvl7 = nullptr, *d_agg = nullptr; u32 *h_agg = nullptr; DevScalars *h_sc = nullptr;
+    u32 shard_rank = 0, shard_n = 1;        // histogram slices sharded over ranks (slimm_gpu_set_shard)
+    bool shard_acc_done = false;
     int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
     std::vector<u32> h_assign;              // host copy of the assign block
     bool h_assign_ok = false;
@@ -392,13 +394,14 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         ctx->launches++;
     }
     {
-        TimeScope ts(ctx, SLIMM_GPU_T_BCOUNT);   // the multisplit: slice starts + unit schedule, then group the items by slice
+        TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);   // the multisplit: slice starts + unit schedule, then group the items by slice
         k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_sched, n_buckets);
         const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
         k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped);
         ctx->launches += 2;
     }
+    if (ctx->shard_n > 1) { CU(cudaGetLastError()); return SLIMM_GPU_OK; }   // the caller exchanges the items, then slimm_gpu_accumulate_items
     {
         CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));   // the histogram was zero-filled on the side stream meanwhile
         TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
@@ -409,7 +412,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
             const u32 per_block = shape && !strncmp(shape, "stride", 6) ? 0u : shape ? (u32)atoi(shape) : 512u;
             const unsigned g = per_block ? (unsigned)std::max<u64>(1, ((u64)n + per_block - 1) / per_block)
                                          : (unsigned)(ctx->sm_count * (shape && !strcmp(shape, "stride8") ? 8 : 16));
-            k_accumulate<<<g, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_sched, ctx->d_hist, per_block);
+            k_accumulate<<<g, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_sched, ctx->d_hist, per_block, 0);
         }
         ctx->launches++;
     }
@@ -419,6 +422,23 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 
 extern "C" {
 
+static u32 n_slices_of(const slimm_gpu_ctx *ctx) { return (u32)((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift); }
+
+// slices [lo, hi) of the histogram owned by rank r of n: contiguous, as even as possible
+static void owned_slices(const slimm_gpu_ctx *ctx, u32 r, u32 *lo, u32 *hi)
+{
+    const u64 ns = n_slices_of(ctx);
+    *lo = (u32)(ns * r / ctx->shard_n); *hi = (u32)(ns * (r + 1) / ctx->shard_n);
+}
+
+static void owned_bins(const slimm_gpu_ctx *ctx, u64 *lo_bin, u64 *hi_bin)
+{
+    u32 lo, hi;
+    owned_slices(ctx, ctx->shard_rank, &lo, &hi);
+    *lo_bin = std::min<u64>(ctx->Bp, (u64)lo << ctx->bucket_shift);
+    *hi_bin = std::min<u64>(ctx->Bp, (u64)hi << ctx->bucket_shift);
+}
+
 static void choose_scatter(slimm_gpu_ctx *ctx)
 {
     // bucketed scatter when the interleaved histogram is much larger than L2 (and bin ids fit 31 bits)
@@ -427,6 +447,7 @@ static void choose_scatter(slimm_gpu_ctx *ctx)
     if (const char *e = getenv("SLIMM_BUCKET_SHIFT")) ctx->bucket_shift = (u32)std::max(16, std::min(28, atoi(e)));   // experiments
     while (((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift) > MAX_BUCKETS) ++ctx->bucket_shift;
     ctx->used_bucket = ctx->n > 0 && ctx->Bp < 0x7FFFFFFFull && (ctx->scatter_mode == 1 || (ctx->scatter_mode == -1 && big));
+    if (ctx->shard_n > 1) ctx->used_bucket = true;   // the items are routed to the ranks that own their slices
 }
 
 static int launch_coverage(slimm_gpu_ctx *ctx)
@@ -437,15 +458,18 @@ static int launch_coverage(slimm_gpu_ctx *ctx)
 
 static int zero_state(slimm_gpu_ctx *ctx)
 {
-    TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
     choose_scatter(ctx);
-    if (!ctx->used_bucket) CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
-    else {   // the big histogram is only needed by k_accumulate: zero-fill it on the side stream, under k_coverage / k_split
+    if (!ctx->used_bucket) {
+        TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
+        CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
+    } else {   // the big histogram is only needed by k_accumulate: zero-fill it on the side stream, under k_coverage / k_split
         CU(cudaEventRecord(ctx->zero_start, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->zero_start, 0));
-        if (ctx->timing) { cudaEventRecord(ctx->ev[SLIMM_GPU_T_SORT][0], ctx->aux_stream); ctx->ev_used[SLIMM_GPU_T_SORT] = true; }   // debug: memset span
-        CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->aux_stream));
-        if (ctx->timing) cudaEventRecord(ctx->ev[SLIMM_GPU_T_SORT][1], ctx->aux_stream);
+        if (ctx->timing) { cudaEventRecord(ctx->ev[SLIMM_GPU_T_ZERO][0], ctx->aux_stream); ctx->ev_used[SLIMM_GPU_T_ZERO] = true; }
+        u64 lo_bin = 0, hi_bin = std::max<u64>(ctx->Bp, 64);
+        if (ctx->shard_n > 1) owned_bins(ctx, &lo_bin, &hi_bin);
+        if (hi_bin > lo_bin) CU(cudaMemsetAsync(ctx->d_hist + lo_bin, 0, (hi_bin - lo_bin) * 8, ctx->aux_stream));
+        if (ctx->timing) cudaEventRecord(ctx->ev[SLIMM_GPU_T_ZERO][1], ctx->aux_stream);
         CU(cudaEventRecord(ctx->zero_done, ctx->aux_stream));
     }
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
@@ -491,7 +515,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
     CU(cudaEventRecord(ctx->upload_done, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) ctx->ev_used[i] = false;
-    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false;
+    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false; ctx->shard_acc_done = false;
     int rc = zero_state(ctx);
     if (rc) return rc;
     if (ctx->n) {
@@ -510,6 +534,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
             if (rc) return rc;
         }
     }
+    else if (ctx->shard_n > 1) CU(cudaMemsetAsync(ctx->d_sched, 0, sizeof(Sched), ctx->stream));   // no records on this rank: no items
     ctx->stage = ST_COVERAGE;
     return SLIMM_GPU_OK;
 }
@@ -536,19 +561,90 @@ int slimm_gpu_set_global_hits(slimm_gpu_ctx *ctx, uint64_t hits)
     return SLIMM_GPU_OK;
 }
 
+int slimm_gpu_set_shard(slimm_gpu_ctx *ctx, uint32_t rank, uint32_t n_ranks)
+{
+    if (!ctx || n_ranks == 0 || rank >= n_ranks) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_CREATED) return fail(ctx, SLIMM_GPU_ESTATE, "set_shard must come before coverage");
+    if (n_ranks > 1 && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "uniq_cov2 bins are not available in sharded runs");
+    if (n_ranks > 1 && ctx->Bp >= 0x7FFFFFFFull) return fail(ctx, SLIMM_GPU_EINVAL, "sharded runs need fewer than 2^31 padded bins");
+    ctx->shard_rank = rank; ctx->shard_n = n_ranks;
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_get_slice_counts(slimm_gpu_ctx *ctx, uint32_t *counts, uint32_t cap, uint32_t *n_slices)
+{
+    if (!ctx || !n_slices) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->used_bucket) return fail(ctx, SLIMM_GPU_ESTATE, "slice counts exist after a bucketed coverage stage");
+    CU(cudaSetDevice(ctx->device));
+    const u32 ns = n_slices_of(ctx);
+    *n_slices = ns;
+    if (counts) {
+        if (cap < ns) return fail(ctx, SLIMM_GPU_EINVAL, "counts buffer too small");
+        CU(cudaMemcpyAsync(counts, reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count), (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_items_device(slimm_gpu_ctx *ctx, void **d_items)
+{
+    if (!ctx || !d_items) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->used_bucket) return fail(ctx, SLIMM_GPU_ESTATE, "grouped items exist after a bucketed coverage stage");
+    *d_items = ctx->d_grouped;
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_accumulate_items(slimm_gpu_ctx *ctx, const uint32_t *d_items, uint64_t n_items)
+{
+    if (!ctx || (n_items && !d_items)) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || ctx->shard_n < 2) return fail(ctx, SLIMM_GPU_ESTATE, "accumulate_items belongs to a sharded run, after coverage");
+    if (n_items > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "too many items");
+    CU(cudaSetDevice(ctx->device));
+    u64 lo_bin = 0, hi_bin = 0;
+    owned_bins(ctx, &lo_bin, &hi_bin);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));    // the owned bins were zero-filled on the side stream
+    if (n_items) {
+        TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
+        const u32 per_block = 512;
+        k_accumulate<<<(unsigned)((n_items + per_block - 1) / per_block), 256, 0, ctx->stream>>>(d_items, nullptr, ctx->d_hist, per_block, (u32)n_items);
+        ctx->launches++;
+    }
+    {
+        TimeScope ts(ctx, SLIMM_GPU_T_STATS);   // partial statistics over the owned bins; the caller sums slimm_gpu_stats_device over ranks
+        CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
+        const u64 s_lo = lo_bin / 64, s_hi = hi_bin / 64;
+        if (s_hi > s_lo) {
+            const u64 n_chunks = (s_hi - s_lo + STATS_STEPS_PER_WARP - 1) / STATS_STEPS_PER_WARP;
+            k_ref_stats<<<grid_for(ctx, n_chunks * 32, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, s_lo, s_hi, ctx->d_off, ctx->G, ctx->d_stats);
+            ctx->launches++;
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->shard_acc_done = true;
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32)
+{
+    if (!ctx || !d_ptr || !n_u32) return SLIMM_GPU_EINVAL;
+    *d_ptr = ctx->d_stats; *n_u32 = (u64)ctx->G * 4;
+    return SLIMM_GPU_OK;
+}
+
 int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
 {
     if (!ctx) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_COVERAGE) return fail(ctx, SLIMM_GPU_ESTATE, "filter needs coverage first");
     CU(cudaSetDevice(ctx->device));
     ctx->q = cov_cut_off; ctx->min_reads_opt = min_reads;
-    {
+    if (ctx->shard_n > 1 && !ctx->shard_acc_done) return fail(ctx, SLIMM_GPU_ESTATE, "sharded run: slimm_gpu_accumulate_items must come before filter");
+    if (ctx->shard_n == 1) {
         TimeScope ts(ctx, SLIMM_GPU_T_STATS);
         CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
         const u64 n_steps = ctx->Bp / 64;
         const u64 n_chunks = (n_steps + STATS_STEPS_PER_WARP - 1) / STATS_STEPS_PER_WARP;
         const int grid = grid_for(ctx, n_chunks * 32, 256, 8);
-        if (n_steps) k_ref_stats<<<grid, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, n_steps, ctx->d_off, ctx->G, ctx->d_stats);
+        if (n_steps) k_ref_stats<<<grid, 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, 0, n_steps, ctx->d_off, ctx->G, ctx->d_stats);
         ctx->launches += 1;
         CU(cudaGetLastError());
     }

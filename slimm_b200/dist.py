@@ -1,0 +1,90 @@
+"""Several GPUs, one process each: the exchange steps around the sharded C ABI.
+
+Reads are sharded by read id (each rank is pushed its reads).  The histogram is sharded by slice
+(2^22 consecutive padded bins): rank r of n owns slices [S*r/n, S*(r+1)/n) - ``owned_slices``.  After
+``slimm_gpu_coverage`` a rank holds its items grouped by slice; ``exchange_items`` routes every item to
+the rank that owns its slice with ONE all-to-all (4 bytes per record); the histogram itself never
+crosses NVLink.  ``run_sharded`` strings the stages together (include/slimm_gpu.h, "several GPUs").
+
+torch.distributed is plumbing here (NCCL over NVLink on the GPUs; gloo on CPU tensors in the tests).
+The reference has no multi-process mode: this layer has no counterpart there.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def owned_slices(n_slices: int, rank: int, n_ranks: int) -> Tuple[int, int]:
+    """Slices [lo, hi) of rank ``rank`` - the same arithmetic as owned_slices() in csrc/slimm_gpu.cu."""
+    return n_slices * rank // n_ranks, n_slices * (rank + 1) // n_ranks
+
+
+def send_splits(slice_counts: Sequence[int], n_ranks: int) -> List[int]:
+    """Items this rank sends to every rank: the grouped buffer is ordered by slice, so the share of rank q is
+    the contiguous block of the slices q owns."""
+    counts = np.asarray(slice_counts, dtype=np.int64)
+    out = []
+    for q in range(n_ranks):
+        lo, hi = owned_slices(counts.size, q, n_ranks)
+        out.append(int(counts[lo:hi].sum()))
+    return out
+
+
+def exchange_items(items, slice_counts: Sequence[int], group=None):
+    """All-to-all of the slice-grouped items (1-D integer tensor, ``sum(slice_counts)`` long).  Returns the
+    tensor of items this rank owns (in source-rank order) and the per-source counts."""
+    import torch
+    import torch.distributed as dist
+    n_ranks = dist.get_world_size(group)
+    splits_out = send_splits(slice_counts, n_ranks)
+    if int(items.numel()) != sum(splits_out):
+        raise ValueError("items length does not match the slice counts")
+    # gloo has no all_to_all for CPU tensors in every build: exchange the counts with all_gather
+    mine = torch.tensor(splits_out, dtype=torch.int64, device=items.device)
+    table = [torch.empty_like(mine) for _ in range(n_ranks)]
+    dist.all_gather(table, mine, group=group)
+    rank = dist.get_rank(group)
+    splits_in = [int(t[rank].item()) for t in table]
+    recv = torch.empty(sum(splits_in), dtype=items.dtype, device=items.device)
+    if items.is_cuda:
+        dist.all_to_all_single(recv, items, output_split_sizes=splits_in, input_split_sizes=splits_out, group=group)
+    else:   # CPU tests (gloo): point-to-point, same result
+        offs_out = np.concatenate([[0], np.cumsum(splits_out)])
+        offs_in = np.concatenate([[0], np.cumsum(splits_in)])
+        reqs = []
+        for q in range(n_ranks):
+            if q == rank:
+                recv[offs_in[q]:offs_in[q + 1]] = items[offs_out[q]:offs_out[q + 1]]
+                continue
+            reqs.append(dist.isend(items[offs_out[q]:offs_out[q + 1]].contiguous(), q, group=group))
+            reqs.append(dist.irecv(recv[offs_in[q]:offs_in[q + 1]], q, group=group))
+        for r in reqs:
+            r.wait()
+    return recv, splits_in
+
+
+def run_sharded(gpu, device, cov_cut_off: float, min_reads: int, global_hits: int, group=None):
+    """coverage -> items all-to-all -> accumulate owned bins -> sum statistics -> filter -> assign -> sum
+    assign block.  ``gpu`` is a :class:`slimm_b200.api.SlimmGpu` with ``set_shard`` done and this rank's
+    records pushed; afterwards ``gpu.summary()`` / ``gpu.profile()`` give the global results on every rank."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    gpu.coverage()
+    counts = gpu.slice_counts()
+    n_items = int(counts.sum(dtype=np.int64))
+    items = api.device_tensor(gpu.items_device(), max(n_items, 1), torch.int32, device)[:n_items]
+    recv, _ = exchange_items(items, counts, group)
+    gpu._keep.append(recv)                       # the library reads it asynchronously on its stream
+    gpu.accumulate_items(recv.data_ptr() if recv.numel() else 0, int(recv.numel()))
+    p, n = gpu.stats_device()
+    dist.all_reduce(api.device_tensor(p, n, torch.int32, device), group=group)
+    p, n = gpu.counters_device()
+    dist.all_reduce(api.device_tensor(p, n, torch.int64, device), group=group)
+    gpu.set_global_hits(global_hits)
+    gpu.filter(cov_cut_off, min_reads)
+    gpu.assign()
+    p, n = gpu.assign_device()
+    dist.all_reduce(api.device_tensor(p, n, torch.int32, device), group=group)
