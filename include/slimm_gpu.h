@@ -231,6 +231,9 @@ int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa
                        const uint8_t *taxa_has_name);
 int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off, slimm_profile_row *rows,
                       uint64_t cap, uint64_t *n);
+/* taxa of the requested rank the last slimm_gpu_profile call dropped for abundance / coverage / missing name
+ * (faild_count of write_abundance, reference src/slimm.hpp:797-801; only printed with -v) */
+int slimm_gpu_profile_failed(slimm_gpu_ctx *ctx, uint32_t *n);
 
 /* 1 when the lineage table is tree-consistent (every taxon on one level with that rank in db.taxid__name, never 0,
  * one parent): slimm_gpu_profile then runs the rank reduction on the device (k_rank_reduce); any other database

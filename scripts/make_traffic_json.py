@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""profiles/traffic.json from the ncu CSVs of scripts/gpu_traffic.sh:
+    python scripts/make_traffic_json.py r1h cfg5=gpurun_out/traffic_r1h_cfg5.csv cfg2=gpurun_out/traffic_r1h_cfg2.csv
+Per workload and kernel group (bench.py's names): DRAM read + write bytes of ONE launch (last launch seen) and the
+bytes per record at that workload's record count."""
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GROUP = {"k_coverage": "coverage", "k_accumulate": "accumulate", "k_ref_stats": "stats", "k_assign": "assign", "k_split": "split",
+         "k_cutoffs_cluster": "cutoff", "k_cutoffs": "cutoff", "k_slice_hist": "accumulate", "k_split2": "split"}
+RECORDS = {"cfg2": 10_000_000, "cfg3": 100_000_000, "cfg4": 100_000_000, "cfg5": 1_000_000_000}
+tag = sys.argv[1]
+out = {"capture": tag, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, bench.py at the full workload size"}
+for spec in sys.argv[2:]:
+    wl, path = spec.split("=")
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]
+    iK, iM, iV, iU = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[1:]:
+        k = r[iK].split("(")[0].replace("void ", "").split("<")[0]
+        if k not in GROUP or not r[iM].startswith("dram__bytes"):
+            continue
+        d = per.setdefault(r[0], {"kernel": k, "bytes": 0.0})
+        d["bytes"] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
+    res = {}
+    for _, d in sorted(per.items(), key=lambda x: int(x[0])):       # later launches overwrite earlier ones
+        res[GROUP[d["kernel"]]] = {"kernel": d["kernel"], "dram_bytes_per_launch": d["bytes"],
+                                   "dram_bytes_per_record": d["bytes"] / RECORDS[wl]}
+    out[wl] = res
+json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print(json.dumps(out, indent=1))

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "slimm_gpu_read_results", "slimm_gpu_enable_timing", "slimm_gpu_get_timings", "slimm_gpu_get_launch_count",
     "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
     "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
-    "slimm_gpu_accumulate_items", "slimm_gpu_stats_device",
+    "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
 ]
 
 
@@ -115,6 +115,7 @@ def load_library():
     lib.slimm_gpu_set_scatter_mode.argtypes = [vp, C.c_int]
     lib.slimm_gpu_set_taxa.argtypes = [vp, u64, vp, vp, vp]
     lib.slimm_gpu_profile.argtypes = [vp, u32, C.c_float, C.POINTER(_Row), u64, C.POINTER(u64)]
+    lib.slimm_gpu_profile_failed.argtypes = [vp, C.POINTER(u32)]
     lib.slimm_gpu_set_shard.argtypes = [vp, u32, u32]
     lib.slimm_gpu_get_slice_counts.argtypes = [vp, vp, u32, C.POINTER(u32)]
     lib.slimm_gpu_items_device.argtypes = [vp, C.POINTER(vp)]

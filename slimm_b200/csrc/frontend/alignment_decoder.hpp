@@ -1,0 +1,574 @@
+// alignment_decoder.hpp - SAM / BAM decoding for the SLIMM hot path, in pipelined host threads.
+//
+// Replaces what the reference does with SeqAn in the record loop of slimm::analyze_alignments (reference
+// src/slimm.hpp:194-213: readRecord, the unmapped / rID == -1 skip, read_name + ".1" / ".2") and in
+// get_avg_read_length (src/misc.hpp:509-522), and turns the string-keyed `reads` map into dense read ids.
+// Output: struct-of-arrays batches {read_id, ref_id, begin_pos} of the KEPT records in file order, which is
+// what slimm_gpu_push takes.
+//
+//   reader (inflate workers for BGZF)  ->  framer (whole lines / whole BAM records)  ->  parse workers
+//        ->  consumer on the calling thread (dense read ids by first appearance, fills the batch)
+//
+// Semantics kept from SeqAn 2.4 (include/seqan/bam_io/read_sam.h:255-396, read_bam.h:194-277):
+//   SAM  rID = index of RNAME among the @SQ lines, "*" -> -1; beginPos = (int32)(uint32)POS - 1
+//   BAM  rID = refID, beginPos = pos, names and lengths from the binary reference list
+//   kept <=> !(flag & 4) && rID != -1;   key = QNAME + (flag & 0x40 ? ".1" : flag & 0x80 ? ".2" : "")
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bytesource.hpp"
+#include "pipeline.hpp"
+
+namespace slimm_fe {
+
+// ---- hashing ------------------------------------------------------------------------------------
+static inline uint64_t mum(uint64_t a, uint64_t b)
+{
+    const __uint128_t r = (__uint128_t)a * b;
+    return (uint64_t)r ^ (uint64_t)(r >> 64);
+}
+static inline uint64_t load_tail(const char *p, size_t n)   // n < 8
+{
+    uint64_t v = 0;
+    memcpy(&v, p, n);
+    return v;
+}
+static inline uint64_t hash_bytes(const char *p, size_t n)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xD6E8FEB86659FD93ull);
+    while (n >= 8) {
+        uint64_t v;
+        memcpy(&v, p, 8);
+        h = mum(h ^ v, 0xA0761D6478BD642Full);
+        p += 8; n -= 8;
+    }
+    h = mum(h ^ load_tail(p, n), 0xE7037ED1A0B428DBull);
+    return h ^ (h >> 29);
+}
+
+// ---- header -------------------------------------------------------------------------------------
+struct AlignmentHeader {
+    std::vector<std::string> names;   // @SQ SN / BAM reference names, in order
+    std::vector<uint32_t> lengths;    // @SQ LN / l_ref
+};
+
+// open-addressing map contig name -> index (RNAME lookup of the SAM text parser)
+class NameIndex {
+public:
+    void build(const std::vector<std::string> &names)
+    {
+        names_ = &names;
+        size_t cap = 16;
+        while (cap < names.size() * 2 + 2) cap <<= 1;
+        slot_.assign(cap, -1);
+        mask_ = cap - 1;
+        for (size_t i = 0; i < names.size(); ++i) {
+            size_t s = hash_bytes(names[i].data(), names[i].size()) & mask_;
+            while (slot_[s] >= 0) {
+                if ((*names_)[slot_[s]] == names[i]) break;   // duplicate @SQ: SeqAn's name cache resolves to the first
+                s = (s + 1) & mask_;
+            }
+            if (slot_[s] < 0) slot_[s] = (int32_t)i;
+        }
+    }
+    int32_t find(const char *p, size_t n) const
+    {
+        size_t s = hash_bytes(p, n) & mask_;
+        while (slot_[s] >= 0) {
+            const std::string &nm = (*names_)[slot_[s]];
+            if (nm.size() == n && memcmp(nm.data(), p, n) == 0) return slot_[s];
+            s = (s + 1) & mask_;
+        }
+        return -1;
+    }
+
+private:
+    const std::vector<std::string> *names_ = nullptr;
+    std::vector<int32_t> slot_;
+    size_t mask_ = 0;
+};
+
+// ---- one parsed chunk ---------------------------------------------------------------------------
+struct ParsedChunk {
+    std::vector<uint64_t> hash;
+    std::vector<uint32_t> key_off, key_len, ref;
+    std::vector<int32_t> pos;
+    std::vector<char> keys;          // read keys back to back
+    uint64_t n_records = 0;          // records seen, kept or not
+    std::string error;
+    void clear() { hash.clear(); key_off.clear(); key_len.clear(); ref.clear(); pos.clear(); keys.clear(); n_records = 0; error.clear(); }
+    size_t size() const { return hash.size(); }
+    void add(const char *name, size_t name_len, uint32_t flag, uint32_t rid, int32_t begin_pos)
+    {
+        const size_t off = keys.size();
+        keys.insert(keys.end(), name, name + name_len);
+        if (flag & 0x40u) { keys.push_back('.'); keys.push_back('1'); }        // reference src/slimm.hpp:205-208
+        else if (flag & 0x80u) { keys.push_back('.'); keys.push_back('2'); }
+        const size_t len = keys.size() - off;
+        key_off.push_back((uint32_t)off); key_len.push_back((uint32_t)len);
+        hash.push_back(hash_bytes(keys.data() + off, len));
+        ref.push_back(rid); pos.push_back(begin_pos);
+    }
+};
+
+struct ParseJob {
+    std::string head;                 // one record stitched together across a chunk boundary (may be empty)
+    std::shared_ptr<Buffer> buf;
+    size_t begin = 0, end = 0;        // whole records inside buf
+};
+
+// ---- SAM text -----------------------------------------------------------------------------------
+static inline bool parse_u32(const char *p, const char *e, uint32_t &out)
+{
+    if (p == e) return false;
+    uint64_t v = 0;
+    for (; p < e; ++p) {
+        if (*p < '0' || *p > '9') return false;
+        v = v * 10 + (uint64_t)(*p - '0');
+        if (v > 0xFFFFFFFFull) return false;
+    }
+    out = (uint32_t)v;
+    return true;
+}
+
+// one alignment line [p, e) without its newline; seq_len (optional) receives the length of SEQ ("*" -> 0)
+static inline bool parse_sam_line(const char *p, const char *e, const NameIndex &idx, ParsedChunk &out, uint32_t *seq_len)
+{
+    if (e > p && e[-1] == '\r') --e;
+    if (p == e) return true;                                    // blank line
+    if (*p == '@') return true;                                 // header line
+    ++out.n_records;
+    const char *t1 = (const char *)memchr(p, '\t', e - p);
+    if (!t1) { out.error = "SAM record with fewer than 4 fields"; return false; }
+    const char *t2 = (const char *)memchr(t1 + 1, '\t', e - t1 - 1);
+    if (!t2) { out.error = "SAM record with fewer than 4 fields"; return false; }
+    const char *t3 = (const char *)memchr(t2 + 1, '\t', e - t2 - 1);
+    if (!t3) { out.error = "SAM record with fewer than 4 fields"; return false; }
+    const char *t4 = (const char *)memchr(t3 + 1, '\t', e - t3 - 1);
+    if (!t4) t4 = e;
+    uint32_t flag = 0, pos1 = 0;
+    if (!parse_u32(t1 + 1, t2, flag) || flag > 0xFFFFu) { out.error = "SAM FLAG is not a 16-bit number"; return false; }
+    if (!parse_u32(t3 + 1, t4, pos1)) { out.error = "SAM POS is not a number"; return false; }
+    if (seq_len) {                                              // SEQ is field 10
+        const char *f = t4;
+        int field = 4;
+        while (f < e && field < 9) { f = (const char *)memchr(f + 1, '\t', e - f - 1); if (!f) { f = e; break; } ++field; }
+        *seq_len = 0;
+        if (f < e && field == 9) {
+            const char *s = f + 1, *se = (const char *)memchr(s, '\t', e - s);
+            if (!se) se = e;
+            *seq_len = (se - s == 1 && *s == '*') ? 0u : (uint32_t)(se - s);
+        }
+    }
+    const char *rn = t2 + 1;
+    const size_t rn_len = (size_t)(t3 - rn);
+    if ((flag & 4u) || (rn_len == 1 && *rn == '*')) return true;   // reference src/slimm.hpp:197-198
+    const int32_t rid = idx.find(rn, rn_len);
+    if (rid < 0) { out.error = "SAM record names a reference that is not in the header: " + std::string(rn, rn_len); return false; }
+    out.add(p, (size_t)(t1 - p), flag, (uint32_t)rid, (int32_t)pos1 - 1);
+    return true;
+}
+
+static inline void parse_sam_range(const char *p, const char *e, const NameIndex &idx, ParsedChunk &out)
+{
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        const char *le = nl ? nl : e;
+        if (!parse_sam_line(p, le, idx, out, nullptr)) return;
+        p = le + 1;
+    }
+}
+
+// ---- BAM ----------------------------------------------------------------------------------------
+static inline uint32_t rd32(const char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+// one record [p, p + 4 + block_size)
+static inline bool parse_bam_record(const char *p, size_t n, uint32_t n_refs, ParsedChunk &out, uint32_t *seq_len)
+{
+    ++out.n_records;
+    if (n < 36) { out.error = "BAM record shorter than its fixed part"; return false; }
+    const int32_t ref_id = (int32_t)rd32(p + 4), pos = (int32_t)rd32(p + 8);
+    const uint32_t l_name = (unsigned char)p[12];
+    const uint32_t flag = rd32(p + 16) >> 16;                   // n_cigar_op (low half) | flag (high half)
+    if (seq_len) *seq_len = rd32(p + 20);
+    if (36 + (size_t)l_name > n || l_name == 0) { out.error = "BAM record with a bad read name length"; return false; }
+    if ((flag & 4u) || ref_id < 0) return true;
+    if ((uint32_t)ref_id >= n_refs) { out.error = "BAM record references a contig beyond the reference list"; return false; }
+    out.add(p + 36, l_name - 1, flag, (uint32_t)ref_id, pos);
+    return true;
+}
+
+static inline void parse_bam_range(const char *p, const char *e, uint32_t n_refs, ParsedChunk &out)
+{
+    while (p + 4 <= e) {
+        const size_t bs = rd32(p);
+        if (p + 4 + bs > e) { out.error = "BAM record crosses its chunk"; return; }
+        if (!parse_bam_record(p, 4 + bs, n_refs, out, nullptr)) return;
+        p += 4 + bs;
+    }
+}
+
+// ---- dense read ids -----------------------------------------------------------------------------
+// key string -> id by first appearance.  Open addressing on the 64-bit key hash; a hit is confirmed against
+// the stored key, so two different names never share an id.
+class ReadIdTable {
+public:
+    ReadIdTable() { slots_.assign(1u << 16, Slot{0, 0}); mask_ = slots_.size() - 1; }
+    void prefetch(uint64_t h) const { __builtin_prefetch(&slots_[h & mask_]); }
+    uint32_t size() const { return (uint32_t)key_off_.size(); }
+    bool full() const { return key_off_.size() >= 0xFFFFFFFEull; }
+    uint32_t lookup_or_insert(uint64_t h, const char *key, uint32_t len)
+    {
+        size_t s = h & mask_;
+        for (;;) {
+            Slot &sl = slots_[s];
+            if (sl.id1 == 0) break;
+            if (sl.hash == h) {
+                const uint32_t id = sl.id1 - 1;
+                if (key_len_[id] == len && memcmp(key_at(id), key, len) == 0) return id;
+            }
+            s = (s + 1) & mask_;
+        }
+        const uint32_t id = (uint32_t)key_off_.size();
+        slots_[s] = Slot{h, id + 1};
+        store_key(key, len);
+        if ((size_t)(id + 1) * 10 > slots_.size() * 6) grow();
+        return id;
+    }
+
+private:
+    struct Slot { uint64_t hash; uint32_t id1; };
+    static const size_t BLOCK = 1u << 24;
+    const char *key_at(uint32_t id) const { const uint64_t o = key_off_[id]; return blocks_[o >> 24].get() + (o & (BLOCK - 1)); }
+    void store_key(const char *key, uint32_t len)
+    {
+        if (blocks_.empty() || used_ + len > BLOCK) {
+            blocks_.emplace_back(new char[std::max<size_t>(BLOCK, len)]);
+            used_ = 0;
+        }
+        memcpy(blocks_.back().get() + used_, key, len);
+        key_off_.push_back(((uint64_t)(blocks_.size() - 1) << 24) | used_);
+        key_len_.push_back(len);
+        used_ += len;
+    }
+    void grow()
+    {
+        std::vector<Slot> old;
+        old.swap(slots_);
+        slots_.assign(old.size() * 2, Slot{0, 0});
+        mask_ = slots_.size() - 1;
+        for (const Slot &o : old)
+            if (o.id1) {
+                size_t s = o.hash & mask_;
+                while (slots_[s].id1) s = (s + 1) & mask_;
+                slots_[s] = o;
+            }
+    }
+    std::vector<Slot> slots_;
+    size_t mask_ = 0;
+    std::vector<std::unique_ptr<char[]>> blocks_;
+    size_t used_ = 0;
+    std::vector<uint64_t> key_off_;
+    std::vector<uint32_t> key_len_;
+};
+
+// ---- the decoder --------------------------------------------------------------------------------
+struct RecordBatch {
+    uint32_t *read_id = nullptr, *ref_id = nullptr;
+    int32_t *begin_pos = nullptr;
+    size_t n = 0, cap = 0;
+};
+
+struct DecodeStats {
+    uint64_t records_in_file = 0, records_kept = 0, reads = 0;
+    double seconds = 0.0;
+};
+
+class AlignmentDecoder {
+public:
+    static const size_t CHUNK = 4u << 20;
+
+    bool open(const std::string &path, std::string &err)
+    {
+        path_ = path;
+        if (!file_.open(path)) { err = "Could not open " + path + "!"; return false; }
+        comp_ = detect_compression(file_);
+        return read_header(err);
+    }
+    const AlignmentHeader &header() const { return header_; }
+    bool is_bam() const { return is_bam_; }
+
+    // get_avg_read_length (reference src/misc.hpp:509-522): mean SEQ length (integer division) over the first
+    // `sample` records that carry a sequence.  Returns false when no record does (the reference divides by zero).
+    bool avg_read_length(uint32_t sample, uint32_t &avg, std::string &err)
+    {
+        uint32_t count = 0, total = 0;
+        ParsedChunk scratch;
+        auto one = [&](const char *p, size_t n) {
+            uint32_t sl = 0;
+            const uint64_t before = scratch.n_records;
+            const bool ok = is_bam_ ? parse_bam_record(p, n, (uint32_t)header_.names.size(), scratch, &sl)
+                                    : parse_sam_line(p, p + n, names_, scratch, &sl);
+            if (!ok) {   // an unknown RNAME does not stop the reference's length sampling; anything else is fatal in SeqAn too
+                if (scratch.error.compare(0, 16, "SAM record names") != 0) { err = scratch.error; return false; }
+                scratch.error.clear();
+            }
+            if (scratch.n_records != before && sl > 0) { total += sl; ++count; }
+            if (scratch.size() > 4096) scratch.clear();
+            return true;
+        };
+        std::unique_ptr<ChunkReader> rd = make_reader(file_, comp_, CHUNK, 1);
+        bool ok = frame(*rd, [&](ParseJob &job) {
+            if (!job.head.empty() && !one(job.head.data(), job.head.size())) return false;
+            const char *p = job.buf ? job.buf->p + job.begin : nullptr, *e = job.buf ? job.buf->p + job.end : nullptr;
+            while (p && p < e && count < sample) {
+                size_t n;
+                if (is_bam_) n = 4 + (size_t)rd32(p);
+                else { const char *nl = (const char *)memchr(p, '\n', e - p); n = nl ? (size_t)(nl - p) : (size_t)(e - p); }
+                if (!one(p, n)) return false;
+                p += n + (is_bam_ ? 0 : 1);
+            }
+            return count < sample;
+        }, err, sample);
+        if (!ok && !err.empty()) return false;
+        if (count == 0) { err = "no record with a sequence: the average read length is undefined"; return false; }
+        avg = total / count;
+        return true;
+    }
+
+    // Decodes the whole file.  sink(batch) is called on the calling thread with every filled batch (and the last,
+    // partial one); it returns the batch to fill next (double buffering is the sink's business).
+    template <class Sink>
+    bool decode(int n_threads, RecordBatch first, Sink &&sink, DecodeStats &st, std::string &err)
+    {
+        n_threads = std::max(1, n_threads);
+        const int n_parse = std::max(1, comp_ == Compression::bgzf ? n_threads / 2 : n_threads - 1);
+        const int n_inflate = std::max(1, n_threads - n_parse);
+        const uint32_t n_refs = (uint32_t)header_.names.size();
+        OrderedStage<ParseJob, ParsedChunk> parse(n_parse, (size_t)n_parse * 3 + 2, [this, n_refs](ParseJob &job, ParsedChunk &out) {
+            const size_t guess = (job.end - job.begin) / (is_bam_ ? 200 : 250) + 16;
+            out.hash.reserve(guess); out.key_off.reserve(guess); out.key_len.reserve(guess); out.ref.reserve(guess); out.pos.reserve(guess);
+            out.keys.reserve(guess * 24);
+            if (!job.head.empty()) {
+                if (is_bam_) parse_bam_record(job.head.data(), job.head.size(), n_refs, out, nullptr);
+                else parse_sam_line(job.head.data(), job.head.data() + job.head.size(), names_, out, nullptr);
+            }
+            if (out.error.empty() && job.buf) {
+                if (is_bam_) parse_bam_range(job.buf->p + job.begin, job.buf->p + job.end, n_refs, out);
+                else parse_sam_range(job.buf->p + job.begin, job.buf->p + job.end, names_, out);
+            }
+        });
+        std::string frame_err;
+        std::thread framer([&] {
+            std::unique_ptr<ChunkReader> rd = make_reader(file_, comp_, CHUNK, n_inflate);
+            frame(*rd, [&](ParseJob &job) { parse.push(std::move(job)); return true; }, frame_err, 0);
+            parse.close();
+        });
+        RecordBatch batch = first;
+        ReadIdTable table;
+        std::string prev_key;
+        uint64_t prev_hash = 0;
+        uint32_t prev_id = 0;
+        bool have_prev = false;
+        ParsedChunk ch;
+        bool ok = true;
+        while (parse.pop(ch)) {
+            if (!ch.error.empty()) { err = ch.error; ok = false; break; }
+            st.records_in_file += ch.n_records;
+            const size_t n = ch.size();
+            for (size_t i = 0; i < n; ++i) {
+                if (i + 8 < n) table.prefetch(ch.hash[i + 8]);
+                const char *key = ch.keys.data() + ch.key_off[i];
+                const uint32_t len = ch.key_len[i];
+                uint32_t id;
+                if (have_prev && ch.hash[i] == prev_hash && prev_key.size() == len && memcmp(prev_key.data(), key, len) == 0) id = prev_id;
+                else {
+                    if (table.full()) { err = "more than 2^32-2 distinct reads"; ok = false; break; }
+                    id = table.lookup_or_insert(ch.hash[i], key, len);
+                    prev_key.assign(key, len); prev_hash = ch.hash[i]; prev_id = id; have_prev = true;
+                }
+                if (batch.n == batch.cap) { batch = sink(batch); batch.n = 0; }
+                batch.read_id[batch.n] = id; batch.ref_id[batch.n] = ch.ref[i]; batch.begin_pos[batch.n] = ch.pos[i];
+                ++batch.n;
+            }
+            if (!ok) break;
+            st.records_kept += n;
+        }
+        if (!ok) parse.abort();
+        framer.join();
+        if (ok && !frame_err.empty()) { err = frame_err; ok = false; }
+        if (ok && batch.n) sink(batch);
+        st.reads = table.size();
+        return ok;
+    }
+
+private:
+    // Cuts the byte stream into jobs of whole records.  emit returns false to stop early.  limit_hint is unused
+    // by the framing itself (the callers stop through emit).
+    template <class Emit>
+    bool frame(ChunkReader &rd, Emit &&emit, std::string &err, uint32_t /*limit_hint*/)
+    {
+        std::string carry;
+        bool in_header = is_bam_;        // the binary header of a BAM still has to be skipped
+        Buffer raw;
+        while (rd.next(raw)) {
+            if (!raw.error.empty()) { err = raw.error; return false; }
+            std::shared_ptr<Buffer> buf = std::make_shared<Buffer>(std::move(raw));
+            size_t begin = 0;
+            if (in_header) {             // accumulate until the header is complete, then continue behind it
+                carry.append(buf->p, buf->n);
+                size_t hdr = 0;
+                AlignmentHeader tmp;
+                if (!parse_bam_header(carry.data(), carry.size(), tmp, hdr)) continue;
+                in_header = false;
+                std::string rest = carry.substr(hdr);
+                carry.clear();
+                buf = std::make_shared<Buffer>();
+                buf->own.reset(new char[rest.size() ? rest.size() : 1]);
+                memcpy(buf->own.get(), rest.data(), rest.size());
+                buf->p = buf->own.get(); buf->n = rest.size();
+            }
+            ParseJob job;
+            const char *p = buf->p, *e = buf->p + buf->n;
+            if (is_bam_) {
+                if (!carry.empty()) {    // finish the record that started in the previous chunk
+                    while (carry.size() < 4 && begin < buf->n) carry.push_back(p[begin++]);
+                    if (carry.size() < 4) continue;
+                    const size_t need = 4 + (size_t)rd32(carry.data());
+                    const size_t take = std::min(need - carry.size(), buf->n - begin);
+                    carry.append(p + begin, take);
+                    begin += take;
+                    if (carry.size() < need) continue;
+                    job.head.swap(carry);
+                    carry.clear();
+                }
+                size_t end = begin;
+                while (end + 4 <= buf->n) {
+                    const size_t bs = rd32(p + end);
+                    if (end + 4 + bs > buf->n) break;
+                    end += 4 + bs;
+                }
+                carry.assign(p + end, buf->n - end);
+                job.buf = buf; job.begin = begin; job.end = end;
+            } else {
+                const char *first_nl = (const char *)memchr(p, '\n', buf->n);
+                if (!first_nl) { carry.append(p, buf->n); continue; }
+                if (!carry.empty()) {
+                    carry.append(p, first_nl - p);
+                    job.head.swap(carry);
+                    carry.clear();
+                    begin = (size_t)(first_nl - p) + 1;
+                }
+                const char *last_nl = (const char *)memrchr(p + begin, '\n', buf->n - begin);
+                const size_t end = last_nl ? (size_t)(last_nl - p) + 1 : begin;
+                carry.assign(p + end, buf->n - end);
+                job.buf = buf; job.begin = begin; job.end = end;
+            }
+            if (!emit(job)) return false;
+        }
+        if (in_header) { err = "truncated BAM header"; return false; }
+        if (!carry.empty()) {
+            if (is_bam_) { err = "truncated BAM record at the end of the file"; return false; }
+            ParseJob job;                // last line without a newline
+            job.head.swap(carry);
+            if (!emit(job)) return false;
+        }
+        return true;
+    }
+
+    static bool parse_bam_header(const char *p, size_t n, AlignmentHeader &h, size_t &hdr_len)
+    {
+        if (n < 12) return false;
+        const size_t l_text = rd32(p + 4);
+        size_t off = 8 + l_text;
+        if (n < off + 4) return false;
+        const uint32_t n_ref = rd32(p + off);
+        off += 4;
+        for (uint32_t i = 0; i < n_ref; ++i) {
+            if (n < off + 4) return false;
+            const size_t l_name = rd32(p + off);
+            if (n < off + 4 + l_name + 4) return false;
+            h.names.emplace_back(p + off + 4, l_name ? l_name - 1 : 0);
+            h.lengths.push_back(rd32(p + off + 4 + l_name));
+            off += 4 + l_name + 4;
+        }
+        hdr_len = off;
+        return true;
+    }
+
+    bool read_header(std::string &err)
+    {
+        std::unique_ptr<ChunkReader> rd = make_reader(file_, comp_, 1u << 20, 1);
+        std::string acc;
+        Buffer b;
+        bool first = true, done = false;
+        while (!done && rd->next(b)) {
+            if (!b.error.empty()) { err = b.error; return false; }
+            acc.append(b.p, b.n);
+            if (first && acc.size() >= 4) { is_bam_ = memcmp(acc.data(), "BAM\1", 4) == 0; first = false; }
+            if (first) continue;
+            if (is_bam_) {
+                size_t hdr = 0;
+                AlignmentHeader tmp;
+                if (parse_bam_header(acc.data(), acc.size(), tmp, hdr)) { header_ = std::move(tmp); done = true; }
+            } else {
+                // the header ends at the first line that does not start with '@'
+                size_t p = 0;
+                bool complete = false;
+                while (p < acc.size()) {
+                    if (acc[p] != '@') { complete = true; break; }
+                    const size_t nl = acc.find('\n', p);
+                    if (nl == std::string::npos) break;
+                    p = nl + 1;
+                }
+                if (complete) done = true;
+            }
+        }
+        if (first) { is_bam_ = false; }
+        if (is_bam_ && !done) { err = path_ + ": truncated BAM header"; return false; }
+        if (!is_bam_) {
+            size_t p = 0;
+            while (p < acc.size() && acc[p] == '@') {
+                size_t nl = acc.find('\n', p);
+                if (nl == std::string::npos) nl = acc.size();
+                size_t le = nl;
+                if (le > p && acc[le - 1] == '\r') --le;
+                if (le - p >= 3 && acc.compare(p, 3, "@SQ") == 0) {
+                    std::string sn;
+                    uint32_t ln = 0;
+                    size_t f = p;
+                    while (f < le) {
+                        size_t t = acc.find('\t', f);
+                        if (t == std::string::npos || t > le) t = le;
+                        if (t - f > 3 && acc.compare(f, 3, "SN:") == 0) sn = acc.substr(f + 3, t - f - 3);
+                        else if (t - f > 3 && acc.compare(f, 3, "LN:") == 0) ln = (uint32_t)strtoull(acc.substr(f + 3, t - f - 3).c_str(), nullptr, 10);
+                        f = t + 1;
+                    }
+                    header_.names.push_back(sn);
+                    header_.lengths.push_back(ln);
+                }
+                p = nl + 1;
+            }
+        }
+        names_.build(header_.names);
+        return true;
+    }
+
+    std::string path_;
+    MappedFile file_;
+    Compression comp_ = Compression::none;
+    bool is_bam_ = false;
+    AlignmentHeader header_;
+    NameIndex names_;
+};
+
+}  // namespace slimm_fe

@@ -99,6 +99,7 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
                         float abundance_cut_off, u32 rk, std::vector<slimm_profile_row> &out)
 {
     out.clear();
+    last_failed = 0;
     if (rk < 1 || rk > 6) return SLIMM_GPU_EINVAL;
     const u32 pr = rk + 1;
     // a taxon's reference set is only ever read if it has a direct count (phase 2 reads it live), is at the
@@ -165,7 +166,7 @@ int ProfilePlan::finish(const u32 *uniq_reads_count2, u32 matches_count, u32 avg
         const u32 p = slot_t[(size_t)kmax[t] * 8 + pr];            // lineage of the last child iterated (std::set order)
         if (!has_s[p]) { has_s[p] = 1; sab[p] = ab; scnt[p] = count[t]; parents.push_back(p); touch(p); }
         else { sab[p] += ab; scnt[p] += count[t]; }
-        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) continue;
+        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) { ++last_failed; continue; }
         slimm_profile_row r;
         r.taxon = vals[t]; r.kind = 0; r.read_count = count[t]; r.first_child = kmin[t]; r.abundance = ab;
         out.push_back(r);
@@ -228,6 +229,7 @@ int ProfilePlan::finish_from_aggregates(const u32 *agg, u32 matches_count, u32 a
                                         float abundance_cut_off, u32 rk, std::vector<slimm_profile_row> &out) const
 {
     out.clear();
+    last_failed = 0;
     if (!consistent || rk < 1 || rk > 6) return SLIMM_GPU_EINVAL;
     const u32 pr = rk + 1;
     const u32 *cnt_r = agg, *kn_r = agg + G, *klen_r = agg + 2 * (size_t)G, *kmin_r = agg + 3 * (size_t)G, *kmax_r = agg + 4 * (size_t)G;
@@ -250,7 +252,7 @@ int ProfilePlan::finish_from_aggregates(const u32 *agg, u32 matches_count, u32 a
         const u32 p = lvl_idx[(size_t)pr * G + kmax_r[j]];         // parent of the last child iterated (std::set order)
         if (!has_s_l[p]) { has_s_l[p] = 1; sab_l[p] = ab; scnt_l[p] = c; }
         else { sab_l[p] += ab; scnt_l[p] += c; }
-        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) continue;
+        if (ab < abundance_cut_off || cov < coverage_cut_off || !named[t]) { ++last_failed; continue; }
         slimm_profile_row r;
         r.taxon = vals[t]; r.kind = 0; r.read_count = c; r.first_child = kmin_r[j]; r.abundance = ab;
         out.push_back(r);

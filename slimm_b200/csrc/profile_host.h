@@ -26,6 +26,7 @@ struct ProfilePlan {
     std::vector<u32> touched, snapshot;
     std::vector<u32> stamp, kmin, kmax;   // duplicate filter over references; smallest / largest member of a normalized set
     u32 epoch = 0;
+    mutable u32 last_failed = 0;        // taxa of the requested rank the last finish* call dropped (write_abundance's faild_count)
     // tree-consistent databases: per-level dense taxon index of every reference and the taxa of each level (ascending)
     bool consistent = false;
     std::vector<u32> lvl_idx;            // [8][G]

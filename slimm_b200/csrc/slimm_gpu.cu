@@ -906,6 +906,14 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
     return SLIMM_GPU_OK;
 }
 
+int slimm_gpu_profile_failed(slimm_gpu_ctx *ctx, uint32_t *n)
+{
+    if (!ctx || !n) return SLIMM_GPU_EINVAL;
+    if (!ctx->plan) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_set_taxa has not been called");
+    *n = ctx->plan->last_failed;
+    return SLIMM_GPU_OK;
+}
+
 // ---- profile tail fed from the context -----------------------------------------------------------
 int slimm_gpu_set_taxa(slimm_gpu_ctx *ctx, uint64_t n_taxa, const uint32_t *taxa_id, const uint8_t *taxa_rank, const uint8_t *taxa_has_name)
 {

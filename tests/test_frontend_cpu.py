@@ -1,0 +1,143 @@
+"""Host side of the drop-in command line (slimm_b200/bin/slimm), no GPU needed: the threaded SAM / BAM decoder
+against the golden record arrays and against an independent Python statement of the reference's record loop
+(reference src/slimm.hpp:194-213, src/misc.hpp:509-522), and the argument handling of src/slimm.cpp:60-180."""
+from __future__ import annotations
+
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import sam_fixtures as sf
+from slimm_b200 import build as native
+from slimm_b200 import synth
+
+CLI = native.CLI
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    native.build()
+    assert os.path.exists(CLI)
+
+
+def decode(path, tmp_path, threads=4):
+    out = str(tmp_path / "dump.bin")
+    r = subprocess.run([CLI, "--threads", str(threads), "--dump-records", out, "none.sldb", str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return sf.load_dump(out)
+
+
+def assert_records(d, rec, names, lengths, avg):
+    assert d["names"] == list(names)
+    assert (d["ref_len"] == np.asarray(lengths, dtype=np.uint32)).all()
+    assert d["avg"] == avg
+    assert d["N"] == rec.read_id.size
+    assert (d["read_id"] == rec.read_id).all() and (d["ref_id"] == rec.ref_id).all() and (d["begin_pos"] == rec.begin_pos).all()
+
+
+@pytest.mark.parametrize("case", [c for c in gu.case_names() if os.path.exists(os.path.join(gu.GOLD, c, "in.sam.gz"))])
+@pytest.mark.parametrize("packed", ["gz", "plain"])
+def test_decoder_matches_golden_records(case, packed, tmp_path):
+    c = gu.load_case(case)
+    src = os.path.join(c.path, "in.sam.gz")
+    if packed == "plain":
+        p = tmp_path / "in.sam"
+        p.write_bytes(gzip.open(src).read())
+        src = str(p)
+    d = decode(src, tmp_path)
+    assert d["names"] == c.contig_names and d["avg"] == c.avg_read_length
+    assert (d["read_id"] == c.read_id).all() and (d["ref_id"] == c.ref_id).all() and (d["begin_pos"] == c.begin_pos).all()
+
+
+def _fixture(n_frag, seed, shuffle=False):
+    """Paired and single reads, secondary hits, unmapped mates, POS 0, reads that reappear later in the file."""
+    rng = np.random.default_rng(seed)
+    G = 37
+    names = [f"NC_{i:06d}.1 contig {i}" if i % 3 else f"gi|{i}|ref|NC_{i:06d}.1|" for i in range(G)]
+    lengths = rng.integers(5_000, 90_000, G)
+    qn, fl, rf, ps = [], [], [], []
+    for r in range(n_frag):
+        kind = r % 7
+        g = int(rng.integers(0, G))
+        q = f"frag{r}"
+        if kind < 3:                         # single-end read with 1..3 hits
+            for j in range(1 + int(rng.integers(0, 3))):
+                qn.append(q); fl.append(0 if j == 0 else 256); rf.append((g + j) % G); ps.append(int(rng.integers(0, 4000)))
+        elif kind < 5:                       # proper pair, both mapped: keys q.1 / q.2
+            qn += [q, q]; fl += [0x1 | 0x2 | 0x40, 0x1 | 0x2 | 0x80]; rf += [g, g]; ps += [int(rng.integers(1, 4000)), int(rng.integers(1, 4000))]
+        elif kind == 5:                      # pair with an unmapped mate (flag 4, RNAME set as mappers do)
+            qn += [q, q]; fl += [0x1 | 0x40 | 0x8, 0x1 | 0x80 | 0x4]; rf += [g, g]; ps += [int(rng.integers(1, 4000))] * 2
+        else:                                # unmapped, no reference
+            qn.append(q); fl.append(4); rf.append(-1); ps.append(0)
+    if n_frag > 50:                          # a name seen long before: "frag3" again at the end
+        qn.append("frag3"); fl.append(256); rf.append(5); ps.append(77)
+    fx = synth.SamFixture(qn, np.asarray(fl), np.asarray(rf), np.asarray(ps))
+    if shuffle:
+        perm = rng.permutation(len(qn))
+        fx = synth.SamFixture([qn[i] for i in perm], fx.flag[perm], fx.ref_id[perm], fx.pos1[perm])
+    return names, lengths, fx
+
+
+@pytest.mark.parametrize("fmt", ["sam", "sam_crlf_noeol", "sam.gz", "sam.bgzf", "bam"])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_decoder_formats_and_chunk_boundaries(fmt, shuffle, tmp_path):
+    # ~26 MB of SAM text / ~17 MB of BAM: several 4 MB pipeline chunks and hundreds of BGZF blocks
+    names, lengths, fx = _fixture(70_000, 11, shuffle)
+    rec = synth.records_from_sam_fixture(fx)
+    if fmt == "bam":
+        p = tmp_path / "in.bam"
+        p.write_bytes(sf.bgzf_compress(sf.bam_bytes(names, lengths, fx.qname, fx.flag, fx.ref_id, fx.pos1), level=1))
+    else:
+        txt = sf.sam_text(names, lengths, fx.qname, fx.flag, fx.ref_id, fx.pos1, crlf="crlf" in fmt,
+                          trailing_newline="noeol" not in fmt).encode()
+        p = tmp_path / ("in.sam" if fmt.startswith("sam") and "." not in fmt else "in." + fmt)
+        p.write_bytes(gzip.compress(txt, 1) if fmt == "sam.gz" else sf.bgzf_compress(txt, level=1) if fmt == "sam.bgzf" else txt)
+    for threads in (1, 6):
+        d = decode(p, tmp_path, threads)
+        assert_records(d, rec, names, lengths, 100)
+        assert d["n_records"] == len(fx.qname) and d["n_reads"] == rec.n_reads
+
+
+def test_avg_read_length_uses_first_records_with_seq(tmp_path):
+    # records without SEQ are skipped, unmapped ones count (src/misc.hpp:509-522); integer division
+    names, lengths = ["c1"], [10_000]
+    qn = [f"r{i}" for i in range(6)]
+    lines = ["@SQ\tSN:c1\tLN:10000"]
+    seqs = ["A" * 10, "*", "A" * 11, "A" * 12, "*", "A" * 20]
+    flags = [0, 0, 4, 0, 0, 0]
+    for q, s, f in zip(qn, seqs, flags):
+        lines.append(f"{q}\t{f}\tc1\t5\t60\t*\t*\t0\t0\t{s}\t*")
+    p = tmp_path / "in.sam"
+    p.write_text("\n".join(lines) + "\n")
+    d = decode(p, tmp_path)
+    assert d["avg"] == (10 + 11 + 12 + 20) // 4 and d["N"] == 5
+
+
+def test_unknown_reference_name_is_an_error(tmp_path):
+    p = tmp_path / "in.sam"
+    p.write_text("@SQ\tSN:c1\tLN:100\nr1\t0\tc2\t5\t60\t*\t*\t0\t0\tACGT\t*\n")
+    r = subprocess.run([CLI, "--dump-records", str(tmp_path / "d.bin"), "x.sldb", str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "not in the header" in r.stderr
+
+
+@pytest.mark.parametrize("args, code, needle", [
+    ([], 1, "Not enough arguments"),
+    (["db.sldb"], 1, "Not enough arguments"),
+    (["db.txt", "in.sam"], 1, "valid file extensions"),
+    (["-cc", "1.5", "db.sldb", "in.sam"], 1, "not in the interval"),
+    (["-ac", "11", "db.sldb", "in.sam"], 1, "not in the interval"),
+    (["-r", "kingdom", "db.sldb", "in.sam"], 1, "allowed values"),
+    (["-w", "abc", "db.sldb", "in.sam"], 1, "cannot be casted"),
+    (["--nope", "db.sldb", "in.sam"], 1, "illegal option"),
+    (["db.sldb", "/nonexistent/in.sam"], 1, "is not a file use -d option"),
+    (["--help"], 0, "SYNOPSIS"),
+    (["--version"], 0, "0.3.4"),
+])
+def test_command_line_errors(args, code, needle):
+    r = subprocess.run([CLI] + args, capture_output=True, text=True)
+    assert r.returncode == code
+    assert needle in r.stderr + r.stdout
