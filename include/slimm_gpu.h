@@ -87,7 +87,9 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx);
 /* New sample against the same contigs/database (directory mode; reference slimm::reset(),
  * src/slimm.hpp:167-188).  bin_width / avg_read_length may change, 0 keeps the old value. */
 int slimm_gpu_reset(slimm_gpu_ctx *ctx, uint32_t bin_width, uint32_t avg_read_length);
-/* Run all kernels on this cudaStream_t (e.g. the caller's framework stream).  NULL: own stream. */
+/* Run all kernels on this cudaStream_t (e.g. the caller's framework stream).  NULL: a library-owned non-blocking
+ * stream; for the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1).  Work the caller orders against
+ * the stages (NCCL reductions of the *_device() buffers) must be issued on the same stream. */
 int slimm_gpu_set_stream(slimm_gpu_ctx *ctx, void *cuda_stream);
 
 /* Pinned host buffers for the decode threads to pack batches into (cudaHostAlloc). */

@@ -188,7 +188,10 @@ class SlimmGpu:
         self.close()
 
     def set_stream(self, cuda_stream: int):
-        self._check(self._lib.slimm_gpu_set_stream(self._ctx, C.c_void_p(cuda_stream)), "set_stream")
+        """Run the stages on the caller's stream.  A framework's default stream has handle 0, which the C ABI reads
+        as "library-owned stream": it is passed as cudaStreamLegacy (0x1) instead, so that the library's kernels and
+        the caller's work (NCCL collectives issued on that stream) stay ordered."""
+        self._check(self._lib.slimm_gpu_set_stream(self._ctx, C.c_void_p(cuda_stream if cuda_stream else 1)), "set_stream")
 
     def reset(self, bin_width: int = 0, avg_read_length: int = 0):
         self._check(self._lib.slimm_gpu_reset(self._ctx, bin_width, avg_read_length), "reset")
@@ -437,4 +440,7 @@ def device_tensor(ptr: int, n: int, dtype, device):
     """Zero-copy torch view of library-owned device memory (for NCCL reductions across ranks)."""
     import torch
     typestr = {torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
-    return torch.as_tensor(_DevicePointer(ptr, n, typestr), device=device)
+    t = torch.as_tensor(_DevicePointer(ptr, n, typestr), device=device)
+    if n and t.data_ptr() != ptr:
+        raise SlimmGpuError("torch.as_tensor copied the device buffer instead of wrapping it")
+    return t

@@ -95,11 +95,14 @@ __device__ __forceinline__ u32 fast_div(u32 n, const BinDiv &d)
     const u32 t = __umulhi(d.mul, n);
     return (t + ((n - t) >> d.s1)) >> d.s2;
 }
-__device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32 upos, u32 half_avg, const BinDiv &wdiv)
+__device__ __forceinline__ u64 bin_of_meta(const uint4 &m /* {len, nb, off_lo, off_hi} */, u32 upos, u32 half_avg, const BinDiv &wdiv)
 {
-    const uint4 m = __ldg(meta + g);   // {len, nb, off_lo, off_hi}
     const u32 center = min(upos + half_avg, m.x);
     return (((u64)m.w << 32) | m.z) + fast_div(center, wdiv);
+}
+__device__ __forceinline__ u64 bin_of(const uint4 *__restrict__ meta, u32 g, u32 upos, u32 half_avg, const BinDiv &wdiv)
+{
+    return bin_of_meta(__ldg(meta + g), upos, half_avg, wdiv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -141,16 +144,33 @@ __device__ __forceinline__ void window_masks(u32 H, u32 E, u32 n_in, u32 p, u32 
     }
 }
 
+// One window's worth of record fields, fetched ahead of their use: k_coverage issues the loads of the window that
+// follows (its start is known as soon as the ballots of the current one are in) before it works through the current
+// one, so the DRAM latency of the three arrays is hidden behind ~150 instructions of independent work.
+struct WinRegs { u32 r, g, upos, nx; };   // nx: read id of the record behind the window (lane 31 only)
+
 template <class Rec>
-__device__ __forceinline__ void load_window(const Rec &rec, u32 p, u32 n, u32 chunk_end, u32 lane, Window &w, u32 &bad)
+__device__ __forceinline__ WinRegs fetch_window(const Rec &rec, u32 p, u32 n, u32 lane)
+{
+    const u32 i = p + lane;
+    const bool in = i < n;
+    WinRegs x;
+    x.r = in ? rec.read(i) : 0u;
+    x.g = in ? rec.refid(i) : 0u;
+    x.upos = in ? rec.upos(i) : 0u;
+    x.nx = (lane == 31 && i + 1 < n) ? rec.read(i + 1) : 0u;
+    return x;
+}
+
+__device__ __forceinline__ void analyse_window(const WinRegs &x, u32 p, u32 n, u32 chunk_end, u32 lane, Window &w, u32 &bad)
 {
     const u32 i = p + lane;
     const bool in = i < n;
     const bool has_nx = i + 1 < n;
-    w.r = in ? rec.read(i) : 0u;
-    w.g = in ? rec.refid(i) : 0u;
+    w.r = x.r;
+    w.g = x.g;
     u32 nx = __shfl_down_sync(FULL, w.r, 1);
-    if (lane == 31 && has_nx) nx = rec.read(i + 1);
+    if (lane == 31) nx = x.nx;
     const u32 pv = __shfl_up_sync(FULL, w.r, 1);
     const bool head = in && (lane == 0 || pv != w.r);
     const bool last = in && (!has_nx || nx != w.r);
@@ -261,7 +281,7 @@ __device__ __noinline__ u32 coverage_long_run(const Rec &rec, u32 p, u32 n, u32 
 }
 
 template <class Rec, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_coverage(Rec rec, u32 n, CovParams P)
 {
     __shared__ u32 s_cnt[MODE ? MAX_BUCKETS : 1];                  // items per histogram slice (shared-memory REDs)
@@ -278,15 +298,21 @@ k_coverage(Rec rec, u32 n, CovParams P)
         u32 p = find_head(rec, c0, n, lane);
         u32 n_cw = 0, n_lr = 0;                                    // compact words / long runs of this chunk (warp-uniform)
         const u64 cw_base = (u64)c * CW_SLOT;
+        WinRegs cur = fetch_window(rec, p, n, lane);
         while (p < c1) {
             Window win;
-            load_window(rec, p, n, c1, lane, win, bad);
+            analyse_window(cur, p, n, c1, lane, win, bad);
             if (win.long_run) {
                 if (lane == 0) ++heads;
                 p = coverage_long_run<Rec, MODE>(rec, p, n, lane, P, s_cnt, uniq, bad, c * LR_SLOT, n_lr);
+                cur = fetch_window(rec, p, n, lane);
                 continue;
             }
             const u32 g = win.g;
+            const bool ok = g < P.G;
+            const uint4 meta = __ldg(P.meta + (ok ? g : 0u));       // issued now, used after the run analysis
+            const u32 upos = cur.upos;
+            cur = fetch_window(rec, win.next, n, lane);            // the next window's loads fly during this window's work
             const u32 gh = __shfl_sync(FULL, g, win.whole ? win.s : (int)lane);
             const u32 Wm = __ballot_sync(FULL, win.whole && g != gh);
             const bool multi = (Wm & win.M) != 0;                  // the read names another reference as well
@@ -308,16 +334,14 @@ k_coverage(Rec rec, u32 n, CovParams P)
                 n_cw += __popc(C);
             }
             u64 b = 0;
-            bool ok = false;
             if (win.whole) {
                 if (is_head) {
                     ++heads; uniq += !multi;
                     if (P.res_kind && !multi) P.res_kind[p + lane] = 3;
                 }
-                ok = g < P.G;
                 if (!ok) { bad |= 2u; if (MODE) __stcs(P.items + p + lane, ITEM_SKIP); }
                 else {
-                    b = bin_of(P.meta, g, rec.upos(p + lane), P.half_avg, P.wdiv);
+                    b = bin_of_meta(meta, upos, P.half_avg, P.wdiv);
                     emit<MODE>(P, p + lane, b, first, multi);
                 }
             }
