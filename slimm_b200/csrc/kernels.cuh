@@ -197,6 +197,7 @@ __device__ __forceinline__ u32 find_head(const Rec &rec, u32 c0, u32 n, u32 lane
 #define PREFETCH_AHEAD 160u  // records between a window and the lines prefetched for the windows after it
 #define CW_SLOT (CHUNK + 32) // compact words a chunk can emit (its last run may reach 31 records past the chunk)
 #define LR_SLOT 64u          // long runs a chunk can own (each is longer than 32 records)
+#define RS_SLOT (CHUNK / 2 + 16) // multi-target reads a chunk can own (each has at least two records)
 #define CW_HEAD 0x80000000u
 #define MAX_BUCKETS 512      // padded bin ids fit 31 bits, slices are >= 2^22 bins
 
@@ -205,6 +206,7 @@ struct CovParams {
     unsigned long long *hist;       // MODE 0
     u32 *items, *bucket_cnt; u32 shift, n_buckets;   // MODE 1
     u32 *cw, *cw_idx; uint2 *chunk_cnt; u32 *lr;     // compact stream of the multi-mapped reads for k_assign
+    unsigned short *rs;                              // per chunk: where every multi-target read starts inside the chunk's compact words
     unsigned char *res_kind;        // optional per-read results: marks the head of every single-target read
     DevScalars *sc;
 };
@@ -296,7 +298,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
     for (u32 c = wg; c < n_chunks; c += nw) {
         const u32 c0 = c * CHUNK, c1 = min(c0 + CHUNK, n);
         u32 p = find_head(rec, c0, n, lane);
-        u32 n_cw = 0, n_lr = 0;                                    // compact words / long runs of this chunk (warp-uniform)
+        u32 n_cw = 0, n_lr = 0, n_rs = 0;                          // compact words / long runs / multi-target reads of this chunk (warp-uniform)
         const u64 cw_base = (u64)c * CW_SLOT;
         WinRegs cur = fetch_window(rec, p, n, lane);
         while (p < c1) {
@@ -326,12 +328,16 @@ k_coverage(Rec rec, u32 n, CovParams P)
                     if (multi && (int)lane - d >= win.s && t == g) first = false;
                 }
                 const u32 C = __ballot_sync(FULL, multi && first); // the compact stream keeps the distinct references
+                const u32 Hm = __ballot_sync(FULL, multi && is_head);
                 if (multi && first) {
-                    const u64 at = cw_base + n_cw + __popc(C & LANE_LT(lane));
+                    const u32 local = n_cw + __popc(C & LANE_LT(lane));
+                    const u64 at = cw_base + local;
                     P.cw[at] = g | (is_head ? CW_HEAD : 0u);
                     if (P.cw_idx) P.cw_idx[at] = p + lane;
+                    if (is_head) P.rs[(u64)c * RS_SLOT + n_rs + __popc(Hm & LANE_LT(lane))] = (unsigned short)local;
                 }
                 n_cw += __popc(C);
+                n_rs += __popc(Hm);
             }
             u64 b = 0;
             if (win.whole) {
@@ -348,7 +354,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
             if (MODE == 1 && win.whole && ok && first) atomicAdd(&s_cnt[(u32)(b >> P.shift)], 1u);
             p = win.next;
         }
-        if (lane == 0) P.chunk_cnt[c] = make_uint2(n_cw, n_lr);
+        if (lane == 0) P.chunk_cnt[c] = make_uint2(n_cw, min(n_lr, 0xFFu) | (n_rs << 8));
     }
     heads = warp_sum(heads); uniq = warp_sum(uniq); bad = warp_or(bad);
     if (lane == 0) { atomicAdd(&s_h, heads); atomicAdd(&s_u, uniq); if (bad) atomicOr(&s_b, bad); }
@@ -1120,7 +1126,141 @@ k_assign(Rec rec, u32 n, AssignParams P)
             }
             p = win.next > p ? win.next : p + 32;
         }
-        for (u32 k = 0; k < cnt.y; ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, s_key, s_val);
+        for (u32 k = 0; k < (cnt.y & 0xFFu); ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, s_key, s_val);
+    }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x)
+        if (s_key[k] != LCA_EMPTY && s_val[k]) atomicAdd(P.lca_cnt + s_key[k], s_val[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5+K6, one THREAD per multi-target read.  k_coverage lists, per chunk, where every multi-target read
+// starts inside the chunk's compact words (rs); a warp takes a chunk and its lanes take 32 reads at a time.
+// A read's few words are fetched four at a time and the lineage rows of all four are requested before any
+// of them is needed, so a read costs two or three memory round trips instead of one per word and level.
+// L16: lineages as 8 x 16-bit per-level dense taxon indices (one 16-byte row per reference; equality of the
+// indices is equality of the taxon ids, zeros included) - used whenever there are fewer than 65536
+// references; otherwise the 8 x 32-bit taxon ids themselves (two 16-byte rows).
+// Reads longer than 32 records are still walked by the whole warp (assign_long_run).
+// ------------------------------------------------------------------------------------------------
+#ifndef ASSIGN_READS_OCC
+#define ASSIGN_READS_OCC 4          // CTAs per SM the register allocation of k_assign_reads is bounded for
+#endif
+struct Lin16 { uint4 v; };
+struct Lin32 { uint4 a, b; };
+__device__ __forceinline__ void lin_load(const uint4 *__restrict__ t, u32 g, Lin16 &o) { o.v = __ldg(t + g); }
+__device__ __forceinline__ void lin_load(const uint4 *__restrict__ t, u32 g, Lin32 &o) { o.a = __ldg(t + 2 * (u64)g); o.b = __ldg(t + 2 * (u64)g + 1); }
+__device__ __forceinline__ void lin_zero(Lin16 &o) { o.v = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void lin_zero(Lin32 &o) { o.a = make_uint4(0, 0, 0, 0); o.b = o.a; }
+// acc |= x ^ y, slot by slot
+__device__ __forceinline__ void lin_acc(Lin16 &acc, const Lin16 &x, const Lin16 &y)
+{
+    acc.v.x |= x.v.x ^ y.v.x; acc.v.y |= x.v.y ^ y.v.y; acc.v.z |= x.v.z ^ y.v.z; acc.v.w |= x.v.w ^ y.v.w;
+}
+__device__ __forceinline__ void lin_acc(Lin32 &acc, const Lin32 &x, const Lin32 &y)
+{
+    acc.a.x |= x.a.x ^ y.a.x; acc.a.y |= x.a.y ^ y.a.y; acc.a.z |= x.a.z ^ y.a.z; acc.a.w |= x.a.w ^ y.a.w;
+    acc.b.x |= x.b.x ^ y.b.x; acc.b.y |= x.b.y ^ y.b.y; acc.b.z |= x.b.z ^ y.b.z; acc.b.w |= x.b.w ^ y.b.w;
+}
+// bit l set: some surviving reference differs from the first one on level l
+__device__ __forceinline__ u32 lin_neq(const Lin16 &acc)
+{
+    const u32 w[4] = {acc.v.x, acc.v.y, acc.v.z, acc.v.w};
+    u32 m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= ((u32)((w[k] & 0xFFFFu) != 0) << (2 * k)) | ((u32)((w[k] >> 16) != 0) << (2 * k + 1));
+    return m;
+}
+__device__ __forceinline__ u32 lin_neq(const Lin32 &acc)
+{
+    return (u32)(acc.a.x != 0) | ((u32)(acc.a.y != 0) << 1) | ((u32)(acc.a.z != 0) << 2) | ((u32)(acc.a.w != 0) << 3) |
+           ((u32)(acc.b.x != 0) << 4) | ((u32)(acc.b.y != 0) << 5) | ((u32)(acc.b.z != 0) << 6) | ((u32)(acc.b.w != 0) << 7);
+}
+
+template <class Rec, class Lin>
+__global__ void __launch_bounds__(256, ASSIGN_READS_OCC)
+k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
+{
+    __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
+    const u32 lane = threadIdx.x & 31;
+    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
+    __syncthreads();
+    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (u32 c = wg; c < n_chunks; c += nw) {
+        const uint2 cnt = __ldg(P.chunk_cnt + c);
+        const u32 m = cnt.x, n_lr = cnt.y & 0xFFu, n_rs = cnt.y >> 8;   // compact words, long runs, multi-target reads of the chunk
+        const u32 *cw = P.cw + (u64)c * CW_SLOT;
+        const unsigned short *rs = rs_all + (u64)c * RS_SLOT;
+        for (u32 k0 = 0; k0 < n_rs; k0 += 32) {
+            const u32 k = k0 + lane;
+            const u32 start = k < n_rs ? (u32)__ldg(rs + k) : m;
+            u32 end = __shfl_down_sync(FULL, start, 1);
+            if (lane == 31) end = k + 1 < n_rs ? (u32)__ldg(rs + k + 1) : m;
+            if (k >= n_rs) continue;
+            u32 g0 = 0, j0 = start, ns = 0, gmax = 0, vmask = 0;  // vmask: which of the read's (at most 32) words survive
+            Lin l0, acc;
+            lin_zero(l0); lin_zero(acc);
+            for (u32 j = start; j < end; j += 4) {
+                u32 g[4]; bool v[4]; Lin l[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) g[d] = j + d < end ? (__ldg(cw + j + d) & ~CW_HEAD) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {                      // the valid bit and the lineage row travel together
+                    v[d] = false;
+                    lin_zero(l[d]);
+                    if (g[d] != 0xFFFFFFFFu) { v[d] = is_valid(P.vb, g[d]); lin_load(lin_tab, g[d], l[d]); }
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    if (v[d]) {
+                        if (ns == 0) { g0 = g[d]; j0 = j + d; l0 = l[d]; }
+                        else lin_acc(acc, l[d], l0);
+                        gmax = max(gmax, g[d]);
+                        vmask |= 1u << (j + d - start);
+                        ++ns;
+                    }
+            }
+            if (ns == 1) {                                         // sole survivor: the read became unique through the filter
+                atomicAdd(P.uniq2_extra + g0, 1u);
+                if (P.cw_idx) {
+                    const u32 lead = P.cw_idx[(u64)c * CW_SLOT + j0];
+                    if (P.cov2) atomicAdd(P.cov2 + bin_of(P.meta, g0, rec.upos(lead), P.half_avg, P.wdiv), 1u);
+                    if (P.res_kind) { const u32 hd = P.cw_idx[(u64)c * CW_SLOT + start]; P.res_kind[hd] = 1; P.res_val[hd] = g0; }
+                }
+            } else if (ns >= 2) {
+                const u32 eq = ~lin_neq(acc) & 0xFFu;
+                const bool fb = eq == 0;                           // no level agrees: slot 7 of the largest reference id
+                const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1), owner = fb ? gmax : g0;
+                // children[lca] U= S: marks are tested before they are written (the hot ones are set early and then only
+                // read, which keeps them shared in L2 instead of bouncing), four tests in flight at a time
+                u32 *mk_base = fb ? P.fb_mark + (u64)__ldg(P.top_idx + owner) * P.G : P.child_mark + level;
+                const u32 mk_stride = fb ? 1u : 8u;
+                while (vmask) {
+                    u32 *mk[4]; u32 old[4];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        mk[d] = nullptr;
+                        if (vmask) {
+                            const u32 b = (u32)__ffs(vmask) - 1u;
+                            vmask &= vmask - 1u;
+                            mk[d] = mk_base + (u64)(__ldg(cw + start + b) & ~CW_HEAD) * mk_stride;
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) old[d] = mk[d] ? *mk[d] : 1u;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) if (old[d] == 0) *mk[d] = 1u;
+                }
+                count_lca(s_key, s_val, P.lca_cnt, owner * 8 + level);
+                if (P.res_kind) {
+                    const u32 hd = P.cw_idx[(u64)c * CW_SLOT + start];
+                    P.res_kind[hd] = 2;
+                    P.res_val[hd] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level);
+                }
+            }
+        }
+        for (u32 k = 0; k < n_lr; ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, s_key, s_val);
     }
     __syncthreads();
     for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x)

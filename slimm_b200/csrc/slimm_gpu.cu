@@ -44,6 +44,9 @@ struct slimm_gpu_ctx {
     u32 *d_items = nullptr, *d_grouped = nullptr; u64 items_cap = 0; u32 bucket_shift = 22;
     Sched *d_sched = nullptr;
     u32 *d_cw = nullptr, *d_cw_idx = nullptr, *d_lr = nullptr; uint2 *d_chunk_cnt = nullptr; u64 cw_chunks = 0;   // compact stream for k_assign
+    unsigned short *d_rs = nullptr;         // starts of the multi-target reads inside every chunk's compact words
+    uint4 *d_lin16 = nullptr;               // lineages as 8 x 16-bit per-level dense taxon indices (fewer than 65536 references)
+    int assign_variant = 1;                 // 1: one thread per multi-target read, 0: sliding windows over the compact words
     BinDiv wdiv{0, 0, 0};
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
     int cutoff_mode = -1;                   // -1 auto (cluster/DSMEM sort when it fits), 1 global-memory sort
@@ -219,6 +222,20 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     if (const char *e = getenv("SLIMM_GPU_TAIL")) ctx->tail_mode = !strcmp(e, "host") ? 1 : -1;
     if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
     CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
+    if (const char *e = getenv("SLIMM_GPU_ASSIGN")) ctx->assign_variant = !strcmp(e, "window") ? 0 : 1;
+    if (G < 65536) {
+        // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
+        std::vector<unsigned short> l16((size_t)G * 8);
+        for (u32 l = 0; l < 8; ++l) {
+            std::map<u32, u32> idx;
+            for (u32 g = 0; g < G; ++g) idx.emplace(ctx->h_lin[(size_t)g * 8 + l], 0);
+            u32 k = 0;
+            for (auto &kv : idx) kv.second = k++;
+            for (u32 g = 0; g < G; ++g) l16[(size_t)g * 8 + l] = (unsigned short)idx[ctx->h_lin[(size_t)g * 8 + l]];
+        }
+        CU(cudaMalloc(&ctx->d_lin16, (size_t)G * 16));
+        CU(cudaMemcpy(ctx->d_lin16, l16.data(), (size_t)G * 16, cudaMemcpyHostToDevice));
+    }
     if (const char *e = getenv("SLIMM_GPU_SCATTER")) ctx->scatter_mode = !strcmp(e, "direct") ? 0 : !strcmp(e, "bucket") ? 1 : -1;
     CU(cudaMalloc(&ctx->d_sc, sizeof(DevScalars)));
     CU(cudaMemcpy(ctx->d_lin, ctx->h_lin.data(), (size_t)G * 32, cudaMemcpyHostToDevice));
@@ -249,6 +266,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
+    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -351,8 +369,9 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     // compact stream of the multi-mapped reads (k_assign's input), one slot per chunk
     const bool want_idx = (ctx->flags & (SLIMM_GPU_KEEP_UNIQ_COV2 | SLIMM_GPU_READ_RESULTS)) != 0;
     if (ctx->cw_chunks < n_chunks) {
-        cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
-        ctx->d_cw = ctx->d_cw_idx = ctx->d_lr = nullptr; ctx->d_chunk_cnt = nullptr; ctx->cw_chunks = 0;
+        cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt); cudaFree(ctx->d_rs);
+        ctx->d_cw = ctx->d_cw_idx = ctx->d_lr = nullptr; ctx->d_chunk_cnt = nullptr; ctx->d_rs = nullptr; ctx->cw_chunks = 0;
+        CU(cudaMalloc(&ctx->d_rs, n_chunks * RS_SLOT * 2));
         CU(cudaMalloc(&ctx->d_cw, n_chunks * CW_SLOT * 4));
         if (want_idx) CU(cudaMalloc(&ctx->d_cw_idx, n_chunks * CW_SLOT * 4));
         CU(cudaMalloc(&ctx->d_lr, n_chunks * LR_SLOT * 4));
@@ -368,7 +387,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
     CovParams P{};
     P.meta = ctx->d_meta; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
-    P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
+    P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr; P.rs = ctx->d_rs;
     P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.sc = ctx->d_sc;
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
@@ -692,11 +711,20 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
         P.G = G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv;
         P.uniq2_extra = uniq2; P.lca_cnt = lca; P.child_mark = cm; P.fb_mark = fb; P.cov2 = ctx->d_cov2;
         P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.res_val = ctx->d_val;
+        static const int asg_ctas = getenv("SLIMM_ASG_CTAS") ? atoi(getenv("SLIMM_ASG_CTAS")) : 8;   // CTAs per SM (experiments)
+        const int rgrid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * asg_ctas));
+        const uint4 *lin32 = (const uint4 *)ctx->d_lin;
         if (ctx->use_sorted) {
-            k_assign<<<grid, 256, 0, ctx->stream>>>(RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted}, n, P);
+            const RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
+            if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+            else if (ctx->d_lin16) k_assign_reads<RecPacked, Lin16><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else k_assign_reads<RecPacked, Lin32><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, (const u32 *)ctx->d_rp_sorted, 2, ctx->d_valid_bits, n);
         } else {
-            k_assign<<<grid, 256, 0, ctx->stream>>>(RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos}, n, P);
+            const RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
+            if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+            else if (ctx->d_lin16) k_assign_reads<RecSoA, Lin16><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else k_assign_reads<RecSoA, Lin32><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, ctx->d_ref, 1, ctx->d_valid_bits, n);
         }
         ctx->launches += 1 + (P.res_kind ? 1 : 0);
