@@ -282,7 +282,8 @@ __device__ __noinline__ u32 coverage_long_run(const Rec &rec, u32 p, u32 n, u32 
     return end;
 }
 
-template <class Rec, int MODE>
+// EXTRA: the optional outputs (record index per compact word, per-read result marks) are wanted
+template <class Rec, int MODE, bool EXTRA>
 __global__ void __launch_bounds__(256, 6)
 k_coverage(Rec rec, u32 n, CovParams P)
 {
@@ -299,7 +300,9 @@ k_coverage(Rec rec, u32 n, CovParams P)
         const u32 c0 = c * CHUNK, c1 = min(c0 + CHUNK, n);
         u32 p = find_head(rec, c0, n, lane);
         u32 n_cw = 0, n_lr = 0, n_rs = 0;                          // compact words / long runs / multi-target reads of this chunk (warp-uniform)
-        const u64 cw_base = (u64)c * CW_SLOT;
+        u32 *const cw_c = P.cw + (u64)c * CW_SLOT;
+        u32 *const cwi_c = EXTRA && P.cw_idx ? P.cw_idx + (u64)c * CW_SLOT : nullptr;
+        unsigned short *const rs_c = P.rs + (u64)c * RS_SLOT;
         WinRegs cur = fetch_window(rec, p, n, lane);
         while (p < c1) {
             Window win;
@@ -321,37 +324,39 @@ k_coverage(Rec rec, u32 n, CovParams P)
             const bool is_head = win.whole && (int)lane == win.s;
             bool first = is_head;
             if (Wm) {                                              // some read with several references: repeat hits need a look
-                if (multi) first = true;
-                const int span = (int)__reduce_max_sync(FULL, multi ? (u32)(win.e - win.s) : 0u);
+                const int dist = multi ? (int)lane - win.s : 0;    // records of my read before me
+                const int span = (int)__reduce_max_sync(FULL, (u32)dist);
+                bool rep = false;
                 for (int d = 1; d <= span; ++d) {                  // the same reference earlier in my read?
                     const u32 t = __shfl_up_sync(FULL, g, d);
-                    if (multi && (int)lane - d >= win.s && t == g) first = false;
+                    rep |= d <= dist && t == g;
                 }
+                first = multi ? !rep : is_head;
                 const u32 C = __ballot_sync(FULL, multi && first); // the compact stream keeps the distinct references
                 const u32 Hm = __ballot_sync(FULL, multi && is_head);
                 if (multi && first) {
                     const u32 local = n_cw + __popc(C & LANE_LT(lane));
-                    const u64 at = cw_base + local;
-                    P.cw[at] = g | (is_head ? CW_HEAD : 0u);
-                    if (P.cw_idx) P.cw_idx[at] = p + lane;
-                    if (is_head) P.rs[(u64)c * RS_SLOT + n_rs + __popc(Hm & LANE_LT(lane))] = (unsigned short)local;
+                    cw_c[local] = g | (is_head ? CW_HEAD : 0u);
+                    if (EXTRA && cwi_c) cwi_c[local] = p + lane;
+                    if (is_head) rs_c[n_rs + __popc(Hm & LANE_LT(lane))] = (unsigned short)local;
                 }
                 n_cw += __popc(C);
                 n_rs += __popc(Hm);
             }
-            u64 b = 0;
+            if (is_head) {
+                ++heads; uniq += !multi;
+                if (EXTRA && P.res_kind && !multi) P.res_kind[p + lane] = 3;
+            }
             if (win.whole) {
-                if (is_head) {
-                    ++heads; uniq += !multi;
-                    if (P.res_kind && !multi) P.res_kind[p + lane] = 3;
-                }
-                if (!ok) { bad |= 2u; if (MODE) __stcs(P.items + p + lane, ITEM_SKIP); }
+                if (!ok) bad |= 2u;
+                const bool put = ok && first;
+                const u64 b = bin_of_meta(meta, upos, P.half_avg, P.wdiv);
+                if (MODE == 0) { if (put) atomicAdd(P.hist + b, multi ? 1ull : 0x100000001ull); }   // cov += 1 [, uniq_cov += 1]
                 else {
-                    b = bin_of_meta(meta, upos, P.half_avg, P.wdiv);
-                    emit<MODE>(P, p + lane, b, first, multi);
+                    __stcs(P.items + p + lane, put ? ((u32)b | (multi ? 0u : 0x80000000u)) : ITEM_SKIP);
+                    if (put) atomicAdd(&s_cnt[(u32)(b >> P.shift)], 1u);
                 }
             }
-            if (MODE == 1 && win.whole && ok && first) atomicAdd(&s_cnt[(u32)(b >> P.shift)], 1u);
             p = win.next;
         }
         if (lane == 0) P.chunk_cnt[c] = make_uint2(n_cw, min(n_lr, 0xFFu) | (n_rs << 8));

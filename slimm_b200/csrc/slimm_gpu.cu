@@ -391,7 +391,8 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.sc = ctx->d_sc;
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        k_coverage<Rec, 0><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        if (want_idx || P.res_kind) k_coverage<Rec, 0, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        else k_coverage<Rec, 0, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
         ctx->launches++;
         CU(cudaGetLastError());
         return SLIMM_GPU_OK;
@@ -409,7 +410,8 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         CU(cudaMemsetAsync(ctx->d_sched, 0, sizeof(Sched), ctx->stream));
         P.items = ctx->d_items; P.shift = shift; P.n_buckets = n_buckets;
         P.bucket_cnt = reinterpret_cast<u32 *>(reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count));
-        k_coverage<Rec, 1><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        if (want_idx || P.res_kind) k_coverage<Rec, 1, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        else k_coverage<Rec, 1, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
         ctx->launches++;
     }
     {
