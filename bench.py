@@ -257,6 +257,11 @@ def main():
 
     if world > 1:
         from slimm_b200 import dist as sdist
+        gpu.set_shard(rank, world)
+        # items travel as peer-to-peer stores inside the split kernel (CUDA IPC over NVLink); NCCL all-to-all otherwise
+        use_p2p = os.environ.get("SLIMM_BENCH_P2P", "1") != "0" and sdist.connect_peers(gpu, dev, wl["N"])
+        base["config"]["exchange"] = "peer-to-peer stores fused into the split kernel" if use_p2p else "NCCL all-to-all of the items"
+    phases = {}   # SLIMM_BENCH_PHASES=1: CUDA-event durations of the exchange steps, summed over all steps (adds a sync per step)
 
     def hot_path():
         """coverage -> filter -> assign -> profile; with several GPUs the items are routed to the rank that owns their
@@ -264,7 +269,7 @@ def main():
         summed over ranks (slimm_b200/dist.py)."""
         if world > 1:
             gpu.set_shard(rank, world)
-            sdist.run_sharded(gpu, dev, wl["cc"], 0, wl["N"])
+            sdist.run_sharded(gpu, dev, wl["cc"], 0, wl["N"], phase_ms=phases if os.environ.get("SLIMM_BENCH_PHASES") else None)
         else:
             gpu.coverage()
             gpu.filter(wl["cc"], 0)
@@ -320,7 +325,7 @@ def main():
     alg = {"coverage": 16.0 * n_local + (0.0 if bucketed else 8.0 * P + 8.0 * U + 8.0 * B),
            "accumulate": 8.0 * P + 8.0 * U + 8.0 * B, "stats": 8.0 * B, "assign": 16.0 * n_local}
     names = {"coverage": "k_coverage", "accumulate": "k_accumulate (+ histogram memset on the side stream)",
-             "stats": "k_ref_stats", "assign": "k_assign"}
+             "stats": "k_ref_stats", "assign": "k_assign_reads"}
     dom = max((k for k in alg if kernel_ms.get(k, 0) > 0), key=lambda k: kernel_ms[k])
     traffic = None
     try:   # DRAM bytes per record of each kernel from the committed ncu capture (profiles/), scaled to this launch
@@ -372,6 +377,8 @@ def main():
             cpu = {"value": None, "unit": "records/s", "cores": 1, "kind": "unavailable", "sample": str(e)[:200]}
 
     if rank == 0:
+        if phases:
+            sys.stderr.write("phases (ms, summed over all resident + e2e steps incl. warm-up): " + json.dumps({k: round(v, 2) for k, v in phases.items()}) + "\n")
         line = dict(base)
         line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": int(launches),
                      "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

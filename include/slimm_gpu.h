@@ -141,6 +141,21 @@ int slimm_gpu_accumulate_items(slimm_gpu_ctx *ctx, const uint32_t *d_items, uint
 /* device pointer to {nz, reads_count, uniq nz, uniq_reads_count}[n_refs] (u32) for the sum over ranks */
 int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
 
+/* ---- the same exchange without NCCL: peer-to-peer stores over NVLink, fused into the split ---------------------------
+ * On one NVLink/NVSwitch box every rank maps every other rank's receive buffer (CUDA IPC) and the multisplit kernel
+ * writes each item straight to the rank that owns its slice, tile by tile - the all-to-all IS the split's store phase.
+ *   once:      slimm_gpu_set_shard; slimm_gpu_p2p_reserve (same capacity on every rank; returns the 64-byte IPC handle);
+ *              exchange the handles; slimm_gpu_p2p_connect(all handles in rank order)
+ *   per sample: slimm_gpu_coverage (stops before the split); all-gather slimm_gpu_get_slice_counts over ranks;
+ *              slimm_gpu_split_to_peers(table [n_ranks][n_slices]); a cross-rank barrier ordered on the stream (all
+ *              splits complete); slimm_gpu_accumulate_received; then as above (sum the statistics, filter, ...).
+ * Inside a receive buffer the items lie slice by slice (sources in rank order inside a slice), so the owner's
+ * accumulate walks one L2-resident slice after the other exactly as in the single-GPU path. */
+int slimm_gpu_p2p_reserve(slimm_gpu_ctx *ctx, uint64_t cap_items, void *ipc_handle_64);
+int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles /* [n_ranks][64] */, uint32_t n_ranks);
+int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts /* [n_ranks][n_slices] */, uint64_t *n_recv);
+int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx);
+
 /* Stage 2 - reference filter.  Replaces none_zero_bin_count / cov_percent / uniq_cov_percent
  * (src/reference_contig.hpp:84-91,148-155), coverage_cut_off / uniq_coverage_cut_off
  * (src/slimm.hpp:328-344,672-688) with get_quantile_cut_off (src/misc.hpp:197-216) and the

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
     "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
     "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
+    "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received",
 ]
 
 
@@ -120,6 +121,10 @@ def load_library():
     lib.slimm_gpu_get_slice_counts.argtypes = [vp, vp, u32, C.POINTER(u32)]
     lib.slimm_gpu_items_device.argtypes = [vp, C.POINTER(vp)]
     lib.slimm_gpu_accumulate_items.argtypes = [vp, vp, u64]
+    lib.slimm_gpu_p2p_reserve.argtypes = [vp, u64, vp]
+    lib.slimm_gpu_p2p_connect.argtypes = [vp, vp, u32]
+    lib.slimm_gpu_split_to_peers.argtypes = [vp, vp, C.POINTER(u64)]
+    lib.slimm_gpu_accumulate_received.argtypes = [vp]
     lib.slimm_gpu_stats_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     lib.slimm_profile_db_is_tree_consistent.argtypes = [u32, vp, u64, vp, vp, vp, C.POINTER(C.c_int)]
     _lib = lib
@@ -264,6 +269,31 @@ class SlimmGpu:
 
     def accumulate_items(self, items_ptr: int, n_items: int):
         self._check(self._lib.slimm_gpu_accumulate_items(self._ctx, C.c_void_p(items_ptr), n_items), "accumulate_items")
+
+    def p2p_reserve(self, cap_items: int) -> bytes:
+        """Allocates the receive buffer of the peer-to-peer item exchange; returns its 64-byte CUDA IPC handle."""
+        h = C.create_string_buffer(64)
+        self._check(self._lib.slimm_gpu_p2p_reserve(self._ctx, cap_items, h), "p2p_reserve")
+        return h.raw
+
+    def p2p_connect(self, handles: bytes, n_ranks: int):
+        """Maps every rank's receive buffer (handles of all ranks in rank order, 64 bytes each)."""
+        if len(handles) != 64 * n_ranks:
+            raise ValueError("need one 64-byte handle per rank")
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self._lib.slimm_gpu_p2p_connect(self._ctx, buf, n_ranks), "p2p_connect")
+        self.p2p = True
+
+    def split_to_peers(self, all_counts: np.ndarray) -> int:
+        """all_counts[n_ranks][n_slices]: items per slice of every rank.  Splits this rank's items straight into the
+        owners' receive buffers; returns how many items this rank receives."""
+        t = np.ascontiguousarray(all_counts, dtype=np.uint32)
+        n = C.c_uint64(0)
+        self._check(self._lib.slimm_gpu_split_to_peers(self._ctx, t.ctypes.data, C.byref(n)), "split_to_peers")
+        return int(n.value)
+
+    def accumulate_received(self):
+        self._check(self._lib.slimm_gpu_accumulate_received(self._ctx), "accumulate_received")
 
     def stats_device(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_uint64()

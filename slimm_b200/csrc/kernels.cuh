@@ -408,11 +408,16 @@ __global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_bu
 // ------------------------------------------------------------------------------------------------
 #define SPLIT_ITEMS 16
 #define SPLIT_TILE (256 * SPLIT_ITEMS)
+// PEER: every slice has its own destination (dest[slice]: where THIS rank's items of the slice go inside the receive
+// buffer of the rank that owns the slice - local memory or a peer's, mapped over NVLink): the all-to-all of a sharded
+// run happens inside the split, tile by tile, as plain stores.
+template <bool PEER>
 __global__ void __launch_bounds__(256)
-k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out)
+k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, u32 *const *__restrict__ dest)
 {
     __shared__ u32 s_cnt[MAX_BUCKETS];         // items of each slice in this tile, then the slice's tile-local start
     __shared__ u32 s_delta[MAX_BUCKETS];       // global start - tile-local start (mod 2^32)
+    __shared__ u32 *s_dst[PEER ? MAX_BUCKETS : 1];   // PEER: destination of the slice's first item of this tile, minus the tile-local start
     __shared__ u32 s_item[SPLIT_TILE];
     __shared__ unsigned short s_bkt[SPLIT_TILE];
     __shared__ u32 s_warp_tot[8];
@@ -460,7 +465,11 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
             const u32 b = tid + h * 256;
             if (b < n_buckets) {
                 s_cnt[b] = excl[h];
-                if (tot[h]) s_delta[b] = atomicAdd(&sd->cursor[b], tot[h]) - excl[h];
+                if (tot[h]) {
+                    const u32 at = atomicAdd(&sd->cursor[b], tot[h]);
+                    s_delta[b] = at - excl[h];
+                    if (PEER) s_dst[b] = dest[b] + (at - sd->start[b]) - excl[h];
+                }
             }
         }
         __syncthreads();
@@ -474,7 +483,8 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
             }
         __syncthreads();
         const u32 total = base;                                // items of this tile (thread-uniform)
-        for (u32 j = tid; j < total; j += 256) out[j + s_delta[s_bkt[j]]] = s_item[j];
+        if (PEER) for (u32 j = tid; j < total; j += 256) s_dst[s_bkt[j]][j] = s_item[j];
+        else for (u32 j = tid; j < total; j += 256) out[j + s_delta[s_bkt[j]]] = s_item[j];
         __syncthreads();
     }
 }

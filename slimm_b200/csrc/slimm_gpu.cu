@@ -75,6 +75,9 @@ struct slimm_gpu_ctx {
     // rank reduction on the device (tree-consistent databases)
     u32 *d_lvl_idx = nullptr, *d_top_lvl7 = nullptr, *d_agg = nullptr; u32 *h_agg = nullptr; DevScalars *h_sc = nullptr;
     u32 shard_rank = 0, shard_n = 1;        // histogram slices sharded over ranks (slimm_gpu_set_shard)
+    // peer-to-peer item exchange: every rank's receive buffer is mapped into every other rank (CUDA IPC over NVLink)
+    u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
+    u32 **d_dest = nullptr;
     bool shard_acc_done = false;
     int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
     std::vector<u32> h_assign;              // host copy of the assign block
@@ -266,7 +269,9 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
-    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16);
+    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest);
+    for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
+    cudaFree(ctx->d_recv);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]); if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]); }
     if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -419,8 +424,11 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         k_bucket_scan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(ctx->d_sched, n_buckets);
         const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
-        k_split<<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped);
-        ctx->launches += 2;
+        if (ctx->shard_n > 1 && ctx->p2p) { ctx->split_pending = true; ctx->launches += 1; }   // slimm_gpu_split_to_peers splits straight into the owners' buffers
+        else {
+            k_split<false><<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped, nullptr);
+            ctx->launches += 2;
+        }
     }
     if (ctx->shard_n > 1) { CU(cudaGetLastError()); return SLIMM_GPU_OK; }   // the caller exchanges the items, then slimm_gpu_accumulate_items
     {
@@ -443,6 +451,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 
 extern "C" {
 
+static int accumulate_owned(slimm_gpu_ctx *ctx, const u32 *d_items, u64 n_items);
 static u32 n_slices_of(const slimm_gpu_ctx *ctx) { return (u32)((ctx->Bp + (1ull << ctx->bucket_shift) - 1) >> ctx->bucket_shift); }
 
 // slices [lo, hi) of the histogram owned by rank r of n: contiguous, as even as possible
@@ -620,6 +629,11 @@ int slimm_gpu_accumulate_items(slimm_gpu_ctx *ctx, const uint32_t *d_items, uint
     if (!ctx || (n_items && !d_items)) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_COVERAGE || ctx->shard_n < 2) return fail(ctx, SLIMM_GPU_ESTATE, "accumulate_items belongs to a sharded run, after coverage");
     if (n_items > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "too many items");
+    return accumulate_owned(ctx, d_items, n_items);
+}
+
+static int accumulate_owned(slimm_gpu_ctx *ctx, const u32 *d_items, u64 n_items)
+{
     CU(cudaSetDevice(ctx->device));
     u64 lo_bin = 0, hi_bin = 0;
     owned_bins(ctx, &lo_bin, &hi_bin);
@@ -643,6 +657,89 @@ int slimm_gpu_accumulate_items(slimm_gpu_ctx *ctx, const uint32_t *d_items, uint
     CU(cudaGetLastError());
     ctx->shard_acc_done = true;
     return SLIMM_GPU_OK;
+}
+
+// ---- peer-to-peer item exchange (one process per GPU on one NVLink/NVSwitch box) ----------------------------------
+int slimm_gpu_p2p_reserve(slimm_gpu_ctx *ctx, uint64_t cap_items, void *ipc_handle_64)
+{
+    if (!ctx || !ipc_handle_64 || cap_items == 0) return SLIMM_GPU_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->recv_cap < cap_items) {
+        if (ctx->p2p) return fail(ctx, SLIMM_GPU_ESTATE, "the receive buffer cannot grow once peers have mapped it");
+        cudaFree(ctx->d_recv); ctx->d_recv = nullptr; ctx->recv_cap = 0;
+        CU(cudaMalloc(&ctx->d_recv, cap_items * 4));
+        ctx->recv_cap = cap_items;
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_recv));
+    memcpy(ipc_handle_64, &h, 64);
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles, uint32_t n_ranks)
+{
+    if (!ctx || !ipc_handles) return SLIMM_GPU_EINVAL;
+    if (n_ranks != ctx->shard_n || n_ranks < 2) return fail(ctx, SLIMM_GPU_ESTATE, "p2p_connect: call slimm_gpu_set_shard first, with the same number of ranks");
+    if (!ctx->d_recv) return fail(ctx, SLIMM_GPU_ESTATE, "p2p_connect: call slimm_gpu_p2p_reserve first");
+    CU(cudaSetDevice(ctx->device));
+    ctx->peer_recv.assign(n_ranks, nullptr);
+    for (u32 q = 0; q < n_ranks; ++q) {
+        if (q == ctx->shard_rank) { ctx->peer_recv[q] = ctx->d_recv; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)ipc_handles + (size_t)q * 64, 64);
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_recv[q] = (u32 *)p;
+    }
+    if (!ctx->d_dest) CU(cudaMalloc(&ctx->d_dest, MAX_BUCKETS * sizeof(u32 *)));
+    ctx->p2p = true;
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts, uint64_t *n_recv)
+{
+    if (!ctx || !all_counts) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->p2p) return fail(ctx, SLIMM_GPU_ESTATE, "split_to_peers belongs to a peer-to-peer sharded run, after coverage");
+    CU(cudaSetDevice(ctx->device));
+    const u32 ns = n_slices_of(ctx), nr = ctx->shard_n, me = ctx->shard_rank;
+    // receive buffer of owner q: its slices in ascending order, inside a slice the source ranks in ascending order
+    std::vector<u32 *> dest(MAX_BUCKETS, nullptr);
+    u64 mine = 0;
+    for (u32 q = 0; q < nr; ++q) {
+        u32 lo, hi;
+        owned_slices(ctx, q, &lo, &hi);
+        u64 off = 0;
+        for (u32 s = lo; s < hi; ++s)
+            for (u32 src = 0; src < nr; ++src) {
+                if (src == me) dest[s] = ctx->peer_recv[q] + off;
+                off += all_counts[(size_t)src * ns + s];
+            }
+        if (off > ctx->recv_cap) return fail(ctx, SLIMM_GPU_ERANGE, "a rank would receive more items than slimm_gpu_p2p_reserve reserved");
+        if (q == me) mine = off;
+    }
+    ctx->n_recv = mine;
+    if (n_recv) *n_recv = mine;
+    if (ctx->split_pending) {
+        TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);
+        CU(cudaMemcpyAsync(ctx->d_dest, dest.data(), MAX_BUCKETS * sizeof(u32 *), cudaMemcpyHostToDevice, ctx->stream));
+        const u32 n = (u32)ctx->n;
+        const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+        const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
+        k_split<true><<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, ctx->bucket_shift, ns, ctx->d_sched, nullptr, ctx->d_dest);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));   // dest is a host vector; and the caller's barrier comes next anyway
+        ctx->split_pending = false;
+    }
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx)
+{
+    if (!ctx) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->p2p) return fail(ctx, SLIMM_GPU_ESTATE, "accumulate_received belongs to a peer-to-peer sharded run, after split_to_peers");
+    return accumulate_owned(ctx, ctx->d_recv, ctx->n_recv);
 }
 
 int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32)

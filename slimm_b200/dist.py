@@ -46,7 +46,7 @@ def exchange_items(items, slice_counts: Sequence[int], group=None):
     table = [torch.empty_like(mine) for _ in range(n_ranks)]
     dist.all_gather(table, mine, group=group)
     rank = dist.get_rank(group)
-    splits_in = [int(t[rank].item()) for t in table]
+    splits_in = [int(v) for v in torch.stack(table)[:, rank].tolist()]   # one device->host copy
     recv = torch.empty(sum(splits_in), dtype=items.dtype, device=items.device)
     if items.is_cuda:
         dist.all_to_all_single(recv, items, output_split_sizes=splits_in, input_split_sizes=splits_out, group=group)
@@ -65,26 +65,99 @@ def exchange_items(items, slice_counts: Sequence[int], group=None):
     return recv, splits_in
 
 
-def run_sharded(gpu, device, cov_cut_off: float, min_reads: int, global_hits: int, group=None):
+_tokens = {}
+
+
+def _barrier_token(device):
+    import torch
+    if device not in _tokens:
+        _tokens[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _tokens[device]
+
+
+def connect_peers(gpu, device, cap_items: int, group=None) -> bool:
+    """Once per context, after ``set_shard``: every rank reserves a receive buffer of ``cap_items`` items and maps all the
+    others' (CUDA IPC; one NVLink/NVSwitch box, one process per GPU).  Returns False - and leaves the NCCL all-to-all path
+    in place - when peer mapping is not available."""
+    import torch
+    import torch.distributed as dist
+    n_ranks = dist.get_world_size(group)
+    ok, handle = 1, b"\0" * 64
+    try:
+        handle = gpu.p2p_reserve(cap_items)
+    except Exception:
+        ok = 0
+    mine = torch.tensor(list(handle) + [ok], dtype=torch.uint8, device=device)
+    table = torch.empty((n_ranks, 65), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(table, mine, group=group)
+    table = table.cpu().numpy()
+    if not table[:, 64].all():
+        return False
+    try:
+        gpu.p2p_connect(table[:, :64].tobytes(), n_ranks)
+        ok = 1
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if not int(flag.item()):
+        gpu.p2p = False
+        return False
+    return True
+
+
+def run_sharded(gpu, device, cov_cut_off: float, min_reads: int, global_hits: int, group=None, phase_ms=None):
     """coverage -> items all-to-all -> accumulate owned bins -> sum statistics -> filter -> assign -> sum
     assign block.  ``gpu`` is a :class:`slimm_b200.api.SlimmGpu` with ``set_shard`` done and this rank's
-    records pushed; afterwards ``gpu.summary()`` / ``gpu.profile()`` give the global results on every rank."""
+    records pushed; afterwards ``gpu.summary()`` / ``gpu.profile()`` give the global results on every rank.
+    ``phase_ms``: optional dict that receives CUDA-event durations of the exchange steps (bench.py)."""
     import torch
     import torch.distributed as dist
     from . import api
+    marks = []
+
+    def mark(name):
+        if phase_ms is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(device))
+            marks.append((name, e))
+
+    mark("start")
     gpu.coverage()
     counts = gpu.slice_counts()
-    n_items = int(counts.sum(dtype=np.int64))
-    items = api.device_tensor(gpu.items_device(), max(n_items, 1), torch.int32, device)[:n_items]
-    recv, _ = exchange_items(items, counts, group)
-    gpu._keep.append(recv)                       # the library reads it asynchronously on its stream
-    gpu.accumulate_items(recv.data_ptr() if recv.numel() else 0, int(recv.numel()))
+    if getattr(gpu, "p2p", False):
+        # the split writes every item straight into its owner's receive buffer (peer memory over NVLink)
+        n_ranks = dist.get_world_size(group)
+        mine = torch.from_numpy(counts.astype(np.int32)).to(device)
+        table = torch.empty((n_ranks, mine.numel()), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        mark("coverage")
+        gpu.split_to_peers(table.cpu().numpy().view(np.uint32))
+        dist.all_reduce(_barrier_token(device), group=group)       # every rank's stores have landed before anyone accumulates
+        mark("split into peers")
+        gpu.accumulate_received()
+    else:
+        n_items = int(counts.sum(dtype=np.int64))
+        items = api.device_tensor(gpu.items_device(), max(n_items, 1), torch.int32, device)[:n_items]
+        mark("coverage+split")
+        recv, _ = exchange_items(items, counts, group)
+        mark("items all-to-all")
+        gpu._keep.append(recv)                       # the library reads it asynchronously on its stream
+        gpu.accumulate_items(recv.data_ptr() if recv.numel() else 0, int(recv.numel()))
+    mark("accumulate+stats")
     p, n = gpu.stats_device()
     dist.all_reduce(api.device_tensor(p, n, torch.int32, device), group=group)
     p, n = gpu.counters_device()
     dist.all_reduce(api.device_tensor(p, n, torch.int64, device), group=group)
+    mark("stats all-reduce")
     gpu.set_global_hits(global_hits)
     gpu.filter(cov_cut_off, min_reads)
     gpu.assign()
+    mark("filter+assign")
     p, n = gpu.assign_device()
     dist.all_reduce(api.device_tensor(p, n, torch.int32, device), group=group)
+    mark("assign all-reduce")
+    if phase_ms is not None:
+        torch.cuda.synchronize(device)
+        for (_, a), (name, b) in zip(marks, marks[1:]):
+            phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b)

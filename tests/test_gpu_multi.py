@@ -27,7 +27,7 @@ def _case(w):
     return contigs, rec, lineage, {t: v for t, v in db.taxid__name.items()}
 
 
-def _worker(rank, world, port, w, out):
+def _worker(rank, world, port, w, p2p, out):
     import torch
     import torch.distributed as dist
     from slimm_b200 import dist as sdist
@@ -44,9 +44,11 @@ def _worker(rank, world, port, w, out):
         with api.SlimmGpu(contigs.lengths, lineage, w, 100, device=rank) as gpu:
             gpu.set_stream(torch.cuda.current_stream().cuda_stream)
             gpu.set_taxa(taxa)
-            for _ in range(2):                       # twice: a context is reused between samples
+            for it in range(2):                      # twice: a context is reused between samples
                 gpu.reset()
                 gpu.set_shard(rank, world)
+                if p2p and it == 0:                  # items travel as peer-to-peer stores inside the split instead of NCCL
+                    assert sdist.connect_peers(gpu, dev, int(rec.read_id.size)), "CUDA IPC peer mapping failed"
                 gpu.push(rec.read_id[a:b], rec.ref_id[a:b], rec.begin_pos[a:b])
                 sdist.run_sharded(gpu, dev, 0.9, 0, int(rec.read_id.size))
                 s = gpu.summary()
@@ -92,8 +94,9 @@ def _worker(rank, world, port, w, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl_all_to_all", "p2p_split"])
 @pytest.mark.parametrize("w", [10, 1000])
-def test_two_gpus_match_oracle(w):
+def test_two_gpus_match_oracle(w, p2p):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -101,7 +104,7 @@ def test_two_gpus_match_oracle(w):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, w, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, w, p2p, out)) for r in range(2)]
     for p in procs:
         p.start()
     results = [out.get(timeout=600) for _ in procs]
