@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the workload's record count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bins", default=os.environ.get("SLIMM_BENCH_BINS", "keep"), choices=["keep", "skip"],
+                    help="keep: the cov/uniq_cov bins are written back to HBM (fetchable, as -co/-ro need); skip: profile-only run")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     wl = dict(WORKLOADS[args.workload])
@@ -249,7 +251,10 @@ def main():
                                            multi_frac=wl["multi_frac"], k_lo=wl["k_lo"], k_hi=wl["k_hi"], neigh=wl["neigh"])
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
-    gpu = api.SlimmGpu(contigs.lengths, lineage, wl["w"], AVG_READ_LEN, device=local_rank)
+    gpu = api.SlimmGpu(contigs.lengths, lineage, wl["w"], AVG_READ_LEN, device=local_rank,
+                       flags=api.SKIP_BINS if args.bins == "skip" else 0)
+    base["config"]["bins"] = ("written back to HBM (fetchable)" if args.bins == "keep" else
+                              "consumed in shared memory, not written back (profile-only run, SLIMM_GPU_SKIP_BINS)")
     gpu.set_stream(stream.cuda_stream)
     gpu.enable_timing(True)
     gpu.set_taxa(taxa_arrays)
@@ -324,7 +329,10 @@ def main():
     bucketed = kernel_ms["accumulate"] > 0
     alg = {"coverage": 16.0 * n_local + (0.0 if bucketed else 8.0 * P + 8.0 * U + 8.0 * B),
            "accumulate": 8.0 * P + 8.0 * U + 8.0 * B, "stats": 8.0 * B, "assign": 16.0 * n_local}
-    names = {"coverage": "k_coverage", "accumulate": "k_accumulate (+ histogram memset on the side stream)",
+    if bucketed and kernel_ms.get("stats", 0) == 0:   # the per-reference scan ran inside the accumulate stage (fine slices in shared memory)
+        alg["accumulate"] += 8.0 * B
+    names = {"coverage": "k_coverage", "accumulate": "k_fine_count + k_fine_split + k_fine_accumulate (bins and per-reference scan in shared memory)"
+             if kernel_ms.get("stats", 0) == 0 else "k_accumulate (+ histogram memset on the side stream)",
              "stats": "k_ref_stats", "assign": "k_assign_reads"}
     dom = max((k for k in alg if kernel_ms.get(k, 0) > 0), key=lambda k: kernel_ms[k])
     traffic = None

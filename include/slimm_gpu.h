@@ -41,6 +41,9 @@ enum {
 /* flags for slimm_gpu_config.flags */
 #define SLIMM_GPU_KEEP_UNIQ_COV2 1u /* also build uniq_cov2 bins (needed by -co / -ro outputs)        */
 #define SLIMM_GPU_READ_RESULTS 2u   /* keep per-read reassignment / LCA results for slimm_gpu_read_results */
+#define SLIMM_GPU_SKIP_BINS 4u      /* profile-only run (no -co / -ro): when the histogram is accumulated slice by slice in
+                                       shared memory, do not write the bins back to HBM; slimm_gpu_fetch_bins and
+                                       slimm_gpu_bins_device are then unavailable.  Results are unchanged. */
 
 typedef struct slimm_gpu_ctx slimm_gpu_ctx;
 

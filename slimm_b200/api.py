@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libslimm_gpu.so")
 
 KEEP_UNIQ_COV2 = 1
 READ_RESULTS = 2
+SKIP_BINS = 4
 TIMING_NAMES = ["sort", "zero", "split", "coverage", "accumulate", "stats", "cutoff", "assign", "tail_host"]
 
 EXPORTED_SYMBOLS = [

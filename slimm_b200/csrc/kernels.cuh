@@ -520,6 +520,245 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 in shared memory.  The slice-grouped items are split once more, into FINE slices of 2^14 bins, whose
+// {cov, uniq_cov} counters (128 KB) fit one SM's shared memory: a CTA then owns a fine slice, applies its
+// items with shared-memory atomics, reduces the per-reference statistics (K3) while the bins are still on
+// chip and writes the slice out once - no zero-fill pass, no read-modify-write through L2, no scan pass.
+//   k_fine_count  items per fine slice (tile-private counters in shared memory: a tile of slice-grouped items
+//                 spans one or two coarse slices, i.e. at most FINE_REL consecutive fine slices; stragglers
+//                 go through global atomics)
+//   k_fine_scan   exclusive scan -> start / write cursor of every fine slice
+//   k_fine_split  the multisplit of k_split, with the fine slices of the tile's coarse slices as buckets
+//   k_fine_accumulate  one CTA per fine slice
+// ------------------------------------------------------------------------------------------------
+#define FINE_SHIFT 14
+#define FINE_BINS (1u << FINE_SHIFT)
+#define FINE_REL MAX_BUCKETS      // fine slices covered by a tile's shared-memory tables
+#define FINE_PRE 12               // items per thread k_fine_accumulate requests before it zero-fills its bins
+
+// first fine slice of the coarse slice the tile's first item belongs to
+__device__ __forceinline__ u32 fine_base(u32 first_item, u32 cshift) { return ((first_item & 0x7FFFFFFFu) >> cshift) << (cshift - FINE_SHIFT); }
+
+__global__ void __launch_bounds__(256)
+k_fine_count(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_given, u32 cshift, u32 *__restrict__ fine_cnt)
+{
+    __shared__ u32 s_cnt[FINE_REL];
+    const u32 n = sd ? sd->total_items : n_given;
+    const u32 tid = threadIdx.x;
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (u32 b = tid; b < FINE_REL; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+        const u64 t0 = tile * SPLIT_TILE;
+        const u32 base = fine_base(__ldg(items + t0), cshift);
+        u32 item[SPLIT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * 256 + tid;
+            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
+        }
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k)
+            if (item[k] != ITEM_SKIP) {
+                const u32 f = (item[k] & 0x7FFFFFFFu) >> FINE_SHIFT;
+                if (f - base < FINE_REL) atomicAdd(&s_cnt[f - base], 1u);
+                else atomicAdd(fine_cnt + f, 1u);
+            }
+        __syncthreads();
+        for (u32 b = tid; b < FINE_REL; b += 256)
+            if (s_cnt[b]) atomicAdd(fine_cnt + base + b, s_cnt[b]);
+        __syncthreads();
+    }
+}
+
+// start[f] = cursor[f] = items before fine slice f; start[n_fine] = all items.  One block.
+__global__ void __launch_bounds__(1024)
+k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor)
+{
+    __shared__ u32 s_warp[32];
+    __shared__ u32 s_run;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (u32 f0 = 0; f0 < n_fine; f0 += 1024) {
+        const u32 f = f0 + tid;
+        const u32 v = f < n_fine ? cnt[f] : 0u;
+        u32 x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        u32 wbase = 0, all = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const u32 t = s_warp[k]; if (k < (int)wid) wbase += t; all += t; }
+        const u32 run = s_run;
+        if (f < n_fine) { const u32 e = run + wbase + x - v; start[f] = e; cursor[f] = e; }
+        __syncthreads();
+        if (tid == 0) s_run = run + all;
+        __syncthreads();
+    }
+    if (tid == 0) start[n_fine] = s_run;
+}
+
+__global__ void __launch_bounds__(256)
+k_fine_split(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
+             u32 *__restrict__ out)
+{
+    __shared__ u32 s_cnt[FINE_REL];            // items of each fine slice in this tile, then the slice's tile-local start
+    __shared__ u32 s_delta[FINE_REL];          // global start - tile-local start (mod 2^32)
+    __shared__ u32 s_item[SPLIT_TILE];
+    __shared__ unsigned short s_bkt[SPLIT_TILE];
+    __shared__ u32 s_warp_tot[8];
+    const u32 n = sd ? sd->total_items : n_given;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (u32 b = tid; b < FINE_REL; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+        const u64 t0 = tile * SPLIT_TILE;
+        const u32 base = fine_base(__ldg(items + t0), cshift);
+        u32 item[SPLIT_ITEMS], where[SPLIT_ITEMS];             // where: bucket << 16 | rank inside (tile, bucket)
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * 256 + tid;
+            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
+        }
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+            where[k] = 0xFFFFFFFFu;
+            if (item[k] != ITEM_SKIP) {
+                const u32 f = (item[k] & 0x7FFFFFFFu) >> FINE_SHIFT;
+                if (f - base < FINE_REL) where[k] = ((f - base) << 16) | atomicAdd(&s_cnt[f - base], 1u);
+                else out[atomicAdd(cursor + f, 1u)] = item[k];     // a tile that spans more than two coarse slices: one by one
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the bucket counts over the tile (two buckets per thread, halves in order)
+        u32 tot[2], excl[2], run = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u32 b = tid + h * 256;
+            tot[h] = s_cnt[b];
+            u32 x = tot[h];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+            if (lane == 31) s_warp_tot[wid] = x;
+            __syncthreads();
+            u32 wbase = 0, all = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
+            excl[h] = run + wbase + x - tot[h];
+            run += all;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u32 b = tid + h * 256;
+            s_cnt[b] = excl[h];
+            if (tot[h]) s_delta[b] = atomicAdd(cursor + base + b, tot[h]) - excl[h];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SPLIT_ITEMS; ++k)
+            if (where[k] != 0xFFFFFFFFu) {
+                const u32 bk = where[k] >> 16;
+                const u32 pos = s_cnt[bk] + (where[k] & 0xFFFFu);
+                s_item[pos] = item[k];
+                s_bkt[pos] = (unsigned short)bk;
+            }
+        __syncthreads();
+        const u32 total = run;                                 // items of this tile that went through the tables
+        for (u32 j = tid; j < total; j += 256) out[j + s_delta[s_bkt[j]]] = s_item[j];
+        __syncthreads();
+    }
+}
+
+// One CTA per fine slice [f_lo + blockIdx.x]: bins in shared memory, items applied with shared atomics, statistics of the
+// references the slice touches (a warp owns 8 consecutive 64-bin steps; a step never straddles two references because
+// the bin offsets are padded to 64), and - when the bins are kept - one coalesced write of the slice.
+__global__ void __launch_bounds__(1024, 1)
+k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u32 f_lo, u64 Bp, const u64 *__restrict__ off, u32 G,
+                  const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
+                  u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */)
+{
+    extern __shared__ u32 sh[];                                // cov[FINE_BINS] | uniq_cov[FINE_BINS]
+    u32 *cov = sh, *uq = sh + FINE_BINS;
+    const u32 f = f_lo + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 lo = __ldg(start + f), hi = __ldg(start + f + 1);
+    if (lo == hi && !hist4) return;                            // nothing landed here and nobody reads the bins
+    const u64 bin0 = (u64)f << FINE_SHIFT;
+    // 256 steps of 64 bins; warp w takes steps 8w .. 8w+7.  Its first reference is looked up now (among the few references
+    // the slice touches), so that the dependent loads are long done when the bins are complete.
+    const u64 step0 = (bin0 >> 6) + wid * 8;
+    const u64 n_steps = Bp >> 6;
+    u32 g = 0, nz = 0, sum = 0, unz = 0, usum = 0;
+    u64 g_end = 0;
+    if (lo != hi && step0 < n_steps) {
+        u32 a = __ldg(fine_ref + f), b = min(__ldg(fine_ref + f + 1) + 1u, G);   // largest g in [a, b) with off[g] <= first bin of my steps
+        const u64 first_bin = step0 << 6;
+        while (b - a > 1) { const u32 mid = (a + b) >> 1; if (__ldg(off + mid) <= first_bin) a = mid; else b = mid; }
+        g = a;
+        g_end = __ldg(off + g + 1);
+    }
+    // the first FINE_PRE items per thread are requested before the bins are zeroed: their DRAM latency hides behind the fill
+    u32 pre[FINE_PRE];
+#pragma unroll
+    for (int k = 0; k < FINE_PRE; ++k) { const u32 i = lo + k * 1024 + tid; pre[k] = i < hi ? __ldcs(fine + i) : ITEM_SKIP; }
+    for (u32 k = tid; k < 2 * FINE_BINS / 4; k += 1024) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FINE_PRE; ++k)
+        if (pre[k] != ITEM_SKIP) {
+            const u32 b = pre[k] & (FINE_BINS - 1);
+            atomicAdd(&cov[b], 1u);
+            if (pre[k] >> 31) atomicAdd(&uq[b], 1u);
+        }
+    for (u32 i0 = lo + FINE_PRE * 1024; i0 < hi; i0 += 4 * 1024) {   // a slice with more items than usual
+        u32 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * 1024 + tid; v[k] = i < hi ? __ldcs(fine + i) : ITEM_SKIP; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (v[k] != ITEM_SKIP) {
+                const u32 b = v[k] & (FINE_BINS - 1);
+                atomicAdd(&cov[b], 1u);
+                if (v[k] >> 31) atomicAdd(&uq[b], 1u);
+            }
+    }
+    __syncthreads();
+    if (step0 >= n_steps) return;
+#pragma unroll 1
+    for (u32 t = 0; t < 8; ++t) {
+        const u64 s = step0 + t;
+        if (s >= n_steps) break;
+        const u32 b = (wid * 8 + t) * 64 + 2 * lane;
+        const uint2 c2 = *reinterpret_cast<const uint2 *>(cov + b), u2 = *reinterpret_cast<const uint2 *>(uq + b);
+        const uint4 v = make_uint4(c2.x, u2.x, c2.y, u2.y);
+        if (hist4) __stcs(hist4 + s * 32 + lane, v);
+        if (lo != hi) {
+            if (s * 64 >= g_end) {
+                nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
+                if (lane == 0 && (nz | unz)) {
+                    atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
+                    if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
+                }
+                nz = sum = unz = usum = 0;
+                while (s * 64 >= g_end) { ++g; g_end = __ldg(off + g + 1); }
+            }
+            nz += (v.x != 0) + (v.z != 0); sum += v.x + v.z;
+            unz += (v.y != 0) + (v.w != 0); usum += v.y + v.w;
+        }
+    }
+    if (lo != hi) {
+        nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
+        if (lane == 0 && (nz | unz)) {
+            atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
+            if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: per-reference segmented reduction over the interleaved bins.  Replaces
 // bins_coverage::none_zero_bin_count (src/reference_contig.hpp:84-91) for cov and uniq_cov and
 // recovers reads_count / uniq_reads_count as the bin sums (each pair adds 1 to exactly one bin).

@@ -78,6 +78,10 @@ struct slimm_gpu_ctx {
     // peer-to-peer item exchange: every rank's receive buffer is mapped into every other rank (CUDA IPC over NVLink)
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
     u32 **d_dest = nullptr;
+    // fine slices: the histogram is accumulated in shared memory, 2^14 bins per CTA (k_fine_*)
+    u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
+    int acc_mode = 1;                       // 1: fine slices in shared memory, 0: 64-bit REDs into L2-resident slices
+    bool stats_done = false;                // the accumulate stage already reduced the per-reference statistics
     bool shard_acc_done = false;
     int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
     std::vector<u32> h_assign;              // host copy of the assign block
@@ -171,6 +175,19 @@ static int layout_bins(slimm_gpu_ctx *ctx)
         if (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2) CU(cudaMalloc(&ctx->d_cov2, std::max<u64>(Bp, 64) * 4));
         ctx->Bp = Bp;
     }
+    {   // the reference that holds the first bin of every fine slice (k_fine_accumulate starts its segment walk there)
+        const u64 n_fine = (Bp + FINE_BINS - 1) >> FINE_SHIFT;
+        std::vector<u32> fr(n_fine + 1);
+        u32 g = 0;
+        for (u64 f = 0; f <= n_fine; ++f) {
+            const u64 bin = std::min(f << FINE_SHIFT, Bp ? Bp - 1 : 0);
+            while (g + 1 < G && ctx->h_off[g + 1] <= bin) ++g;
+            fr[f] = g;
+        }
+        cudaFree(ctx->d_fine_ref); ctx->d_fine_ref = nullptr;
+        CU(cudaMalloc(&ctx->d_fine_ref, (n_fine + 1) * 4));
+        CU(cudaMemcpy(ctx->d_fine_ref, fr.data(), (n_fine + 1) * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(ctx->d_meta, meta.data(), (size_t)G * sizeof(uint4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_off, ctx->h_off.data(), ((size_t)G + 1) * 8, cudaMemcpyHostToDevice));
     return SLIMM_GPU_OK;
@@ -225,6 +242,9 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     if (const char *e = getenv("SLIMM_GPU_TAIL")) ctx->tail_mode = !strcmp(e, "host") ? 1 : -1;
     if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
     CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
+    if (const char *e = getenv("SLIMM_GPU_ACC")) ctx->acc_mode = !strcmp(e, "l2") ? 0 : 1;
+    if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "SLIMM_GPU_SKIP_BINS and SLIMM_GPU_KEEP_UNIQ_COV2 exclude each other");
+    CU(cudaFuncSetAttribute(k_fine_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
     if (const char *e = getenv("SLIMM_GPU_ASSIGN")) ctx->assign_variant = !strcmp(e, "window") ? 0 : 1;
     if (G < 65536) {
         // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
@@ -270,6 +290,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest);
+    cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref);
     for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
     cudaFree(ctx->d_recv);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
@@ -364,6 +385,44 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
 // histogram slices of 2^22 bins (32 MB of interleaved u64) stay L2-resident while their items are applied
 #define BUCKET_SHIFT 22
 
+// Accumulate + per-reference statistics in shared memory, fine slice by fine slice.  items: grouped by coarse slice
+// (their number is sd->total_items on the device, or n_given); n_cap bounds it on the host; out_buf receives the items
+// grouped by fine slice; [lo_bin, hi_bin) are the bins this rank owns.
+static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd, u64 n_given, u64 n_cap, u32 *out_buf, u64 lo_bin, u64 hi_bin)
+{
+    const u64 n_fine = (ctx->Bp + FINE_BINS - 1) >> FINE_SHIFT;
+    if (ctx->fine_slices_cap < n_fine) {
+        cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor);
+        ctx->d_fine_cnt = ctx->d_fine_start = ctx->d_fine_cursor = nullptr; ctx->fine_slices_cap = 0;
+        CU(cudaMalloc(&ctx->d_fine_cnt, (n_fine + 1) * 4)); CU(cudaMalloc(&ctx->d_fine_start, (n_fine + 1) * 4));
+        CU(cudaMalloc(&ctx->d_fine_cursor, (n_fine + 1) * 4));
+        ctx->fine_slices_cap = n_fine;
+    }
+    TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
+    CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 1) * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
+    const u64 n_tiles = (n_cap + SPLIT_TILE - 1) / SPLIT_TILE;
+    if (n_tiles) {
+        const int cgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 8));
+        k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
+    }
+    k_fine_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor);
+    if (n_tiles) {
+        const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
+        k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
+    }
+    const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
+    if (f_hi > f_lo) {
+        uint4 *hist4 = (ctx->flags & SLIMM_GPU_SKIP_BINS) ? nullptr : (uint4 *)ctx->d_hist;
+        k_fine_accumulate<<<(unsigned)(f_hi - f_lo), 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, ctx->Bp, ctx->d_off, ctx->G,
+                                                                                          ctx->d_fine_ref, ctx->d_stats, hist4);
+    }
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    ctx->stats_done = true;
+    return SLIMM_GPU_OK;
+}
+
 template <class Rec>
 static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
@@ -431,6 +490,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         }
     }
     if (ctx->shard_n > 1) { CU(cudaGetLastError()); return SLIMM_GPU_OK; }   // the caller exchanges the items, then slimm_gpu_accumulate_items
+    if (ctx->acc_mode == 1) return fine_accumulate(ctx, ctx->d_grouped, ctx->d_sched, 0, n, ctx->d_items, 0, ctx->Bp);
     {
         CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));   // the histogram was zero-filled on the side stream meanwhile
         TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
@@ -492,6 +552,8 @@ static int zero_state(slimm_gpu_ctx *ctx)
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_ZERO);
         CU(cudaMemsetAsync(ctx->d_hist, 0, std::max<u64>(ctx->Bp, 64) * 8, ctx->stream));
+    } else if (ctx->acc_mode == 1) {
+        // fine slices: every CTA of k_fine_accumulate writes its whole slice - nothing to zero-fill
     } else {   // the big histogram is only needed by k_accumulate: zero-fill it on the side stream, under k_coverage / k_split
         CU(cudaEventRecord(ctx->zero_start, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->zero_start, 0));
@@ -545,7 +607,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
     CU(cudaEventRecord(ctx->upload_done, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) ctx->ev_used[i] = false;
-    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false; ctx->shard_acc_done = false;
+    ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false; ctx->shard_acc_done = false; ctx->stats_done = false;
     int rc = zero_state(ctx);
     if (rc) return rc;
     if (ctx->n) {
@@ -572,6 +634,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
 int slimm_gpu_bins_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32)
 {
     if (!ctx || !d_ptr || !n_u32) return SLIMM_GPU_EINVAL;
+    if (ctx->flags & SLIMM_GPU_SKIP_BINS) return fail(ctx, SLIMM_GPU_EINVAL, "the bins are not kept (SLIMM_GPU_SKIP_BINS)");
     *d_ptr = ctx->d_hist; *n_u32 = ctx->Bp * 2;
     return SLIMM_GPU_OK;
 }
@@ -637,6 +700,17 @@ static int accumulate_owned(slimm_gpu_ctx *ctx, const u32 *d_items, u64 n_items)
     CU(cudaSetDevice(ctx->device));
     u64 lo_bin = 0, hi_bin = 0;
     owned_bins(ctx, &lo_bin, &hi_bin);
+    if (ctx->acc_mode == 1) {
+        if (ctx->fine_cap < n_items) {
+            cudaFree(ctx->d_fine); ctx->d_fine = nullptr; ctx->fine_cap = 0;
+            CU(cudaMalloc(&ctx->d_fine, std::max<u64>(n_items + n_items / 8, 1024) * 4));
+            ctx->fine_cap = n_items + n_items / 8;
+        }
+        int rc = fine_accumulate(ctx, d_items, nullptr, n_items, n_items, ctx->d_fine, lo_bin, hi_bin);
+        if (rc) return rc;
+        ctx->shard_acc_done = true;
+        return SLIMM_GPU_OK;
+    }
     CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));    // the owned bins were zero-filled on the side stream
     if (n_items) {
         TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
@@ -756,7 +830,7 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
     CU(cudaSetDevice(ctx->device));
     ctx->q = cov_cut_off; ctx->min_reads_opt = min_reads;
     if (ctx->shard_n > 1 && !ctx->shard_acc_done) return fail(ctx, SLIMM_GPU_ESTATE, "sharded run: slimm_gpu_accumulate_items must come before filter");
-    if (ctx->shard_n == 1) {
+    if (ctx->shard_n == 1 && !ctx->stats_done) {
         TimeScope ts(ctx, SLIMM_GPU_T_STATS);
         CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
         const u64 n_steps = ctx->Bp / 64;
@@ -975,6 +1049,7 @@ int slimm_gpu_fetch_bins(slimm_gpu_ctx *ctx, int which, uint32_t ref, uint32_t *
     if (!ctx || !out || ref >= ctx->G || which < 0 || which > 2) return SLIMM_GPU_EINVAL;
     if (ctx->stage < ST_COVERAGE) return fail(ctx, SLIMM_GPU_ESTATE, "coverage has not run");
     if (which == 2 && !ctx->d_cov2) return fail(ctx, SLIMM_GPU_EINVAL, "uniq_cov2 needs SLIMM_GPU_KEEP_UNIQ_COV2");
+    if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && ctx->used_bucket && ctx->acc_mode == 1) return fail(ctx, SLIMM_GPU_EINVAL, "the bins were not kept (SLIMM_GPU_SKIP_BINS)");
     CU(cudaSetDevice(ctx->device));
     const u32 nb = ctx->h_len[ref] / ctx->w + 1u;
     if (cap < nb) return fail(ctx, SLIMM_GPU_EINVAL, "output buffer smaller than the number of bins");
