@@ -414,8 +414,10 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
         uint4 *hist4 = (ctx->flags & SLIMM_GPU_SKIP_BINS) ? nullptr : (uint4 *)ctx->d_hist;
-        k_fine_accumulate<<<(unsigned)(f_hi - f_lo), 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, ctx->Bp, ctx->d_off, ctx->G,
-                                                                                          ctx->d_fine_ref, ctx->d_stats, hist4);
+        u32 *ticket = ctx->d_fine_cnt + n_fine;                // spare word behind the counts (zeroed with them)
+        const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
+        k_fine_accumulate<<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off, ctx->G,
+                                                                         ctx->d_fine_ref, ctx->d_stats, hist4, ticket);
     }
     ctx->launches += 4;
     CU(cudaGetLastError());
