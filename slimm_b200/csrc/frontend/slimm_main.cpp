@@ -399,7 +399,7 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
     memset(&cfg, 0, sizeof cfg);
     cfg.n_refs = G; cfg.ref_len = hd.lengths.data(); cfg.lineage = lineage.data(); cfg.bin_width = opt.bin_width;
     cfg.avg_read_length = avg_read_length; cfg.device = opt.device;
-    cfg.flags = (opt.raw_output || opt.coverage_output) ? SLIMM_GPU_KEEP_UNIQ_COV2 : 0u;
+    cfg.flags = (opt.raw_output || opt.coverage_output) ? SLIMM_GPU_KEEP_UNIQ_COV2 : SLIMM_GPU_SKIP_BINS;   // profile-only runs never read the bins back
     slimm_gpu_ctx *ctx = nullptr;
     int rc = slimm_gpu_create(&cfg, &ctx);
     if (rc != SLIMM_GPU_OK) {

@@ -215,3 +215,49 @@ def test_alternative_paths_agree(env, value, monkeypatch):
     half = len(out) // 2
     assert out[:half] == out[half:]
     assert len(out[0]) > 10
+
+
+@pytest.mark.parametrize("env,value", [("SLIMM_GPU_ACC", "l2"), ("SLIMM_GPU_ASSIGN", "window")])
+def test_alternative_kernels_agree(env, value, monkeypatch):
+    """The older kernels stay selectable for A/B runs (64-bit REDs into L2-resident slices instead of the shared-memory
+    fine slices; sliding-window assign instead of one thread per read): same results, bins included."""
+    contigs, rec, lineage = _synthetic(300, 1_500_000, 5, len_lo=300_000, len_hi=900_000, multi_frac=0.4)
+    w = 10
+    res = oracle.run(contigs.lengths, lineage, w, 100, 0.9, rec.read_id, rec.ref_id, rec.begin_pos)
+    monkeypatch.setenv(env, value)
+    with api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
+        gpu.set_scatter_mode(1)
+        gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
+        gpu.run(0.9)
+        compare_with_oracle(gpu, res, lineage, check_bins=False)
+        for g in (0, 150, 299):
+            a, b = int(res.bin_off[g]), int(res.bin_off[g + 1])
+            np.testing.assert_array_equal(gpu.fetch_bins(0, g), res.cov[a:b])
+            np.testing.assert_array_equal(gpu.fetch_bins(1, g), res.uniq_cov[a:b])
+
+
+def test_skip_bins_profile_only_run():
+    """SLIMM_GPU_SKIP_BINS: the bins live in shared memory only - every statistic and the profile are unchanged, the
+    bins themselves cannot be fetched."""
+    contigs, rec, lineage = _synthetic(300, 1_500_000, 6, len_lo=300_000, len_hi=900_000, multi_frac=0.4)
+    w = 10
+    res = oracle.run(contigs.lengths, lineage, w, 100, 0.9, rec.read_id, rec.ref_id, rec.begin_pos)
+    with api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.SKIP_BINS) as gpu:
+        gpu.set_scatter_mode(1)
+        for _ in range(2):
+            gpu.reset()
+            gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
+            gpu.run(0.9)
+            s = gpu.summary()
+            assert (s.hits_count, s.matches_count, s.uniq_matches_count, s.uniq_matches_count2, s.n_valid) == \
+                   (res.hits, res.n_reads, res.n_uniq, res.n_uniq2, res.n_valid)
+            assert np.float32(s.coverage_cut_off).tobytes() == np.float32(res.cut).tobytes()
+            st = gpu.ref_stats()
+            for x, y in ((st.reads_count, res.reads_count), (st.uniq_reads_count, res.uniq_reads_count), (st.nz_bins, res.nz),
+                         (st.uniq_nz_bins, res.unz), (st.uniq_reads_count2, res.uniq_reads_count2), (st.valid, res.valid)):
+                np.testing.assert_array_equal(x, y)
+            assert gpu.lca_counts() == res.direct
+            with pytest.raises(api.SlimmGpuError):
+                gpu.fetch_bins(0, 0)
+    with pytest.raises(api.SlimmGpuError):
+        api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.SKIP_BINS | api.KEEP_UNIQ_COV2)
