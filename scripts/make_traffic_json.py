@@ -10,7 +10,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GROUP = {"k_coverage": "coverage", "k_accumulate": "accumulate", "k_ref_stats": "stats", "k_assign": "assign", "k_split": "split",
-         "k_cutoffs_cluster": "cutoff", "k_cutoffs": "cutoff", "k_slice_hist": "accumulate", "k_split2": "split"}
+         "k_cutoffs_cluster": "cutoff", "k_cutoffs": "cutoff", "k_assign_reads": "assign", "k_fine_count": "accumulate",
+         "k_fine_scan": "accumulate", "k_fine_split": "accumulate", "k_fine_accumulate": "accumulate"}
 RECORDS = {"cfg2": 10_000_000, "cfg3": 100_000_000, "cfg4": 100_000_000, "cfg5": 1_000_000_000}
 tag = sys.argv[1]
 out = {"capture": tag, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, bench.py at the full workload size"}
@@ -27,10 +28,16 @@ for spec in sys.argv[2:]:
             continue
         d = per.setdefault(r[0], {"kernel": k, "bytes": 0.0})
         d["bytes"] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
+    last = {}
+    for _, d in sorted(per.items(), key=lambda x: int(x[0])):       # later launches overwrite earlier ones, kernel by kernel
+        last[d["kernel"]] = d["bytes"]
     res = {}
-    for _, d in sorted(per.items(), key=lambda x: int(x[0])):       # later launches overwrite earlier ones
-        res[GROUP[d["kernel"]]] = {"kernel": d["kernel"], "dram_bytes_per_launch": d["bytes"],
-                                   "dram_bytes_per_record": d["bytes"] / RECORDS[wl]}
+    for k, b in last.items():                                       # a group is the sum of its kernels (one launch each per step)
+        g = res.setdefault(GROUP[k], {"kernel": [], "dram_bytes_per_launch": 0.0})
+        g["kernel"].append(k); g["dram_bytes_per_launch"] += b
+    for g in res.values():
+        g["kernel"] = " + ".join(sorted(g["kernel"]))
+        g["dram_bytes_per_record"] = g["dram_bytes_per_launch"] / RECORDS[wl]
     out[wl] = res
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
