@@ -130,7 +130,7 @@ def profile_tail(api, gpu, contigs, lineage, taxa_arrays, cc):
     return gpu.summary(), n_rows
 
 
-def run_reference_sample(wl, n_sample, steps, warmup, tmp_root=None):
+def run_reference_sample(wl, n_sample, steps, warmup, tmp_root=None, with_cli=False):
     """Times the UNMODIFIED reference binary (oracle/_ref/slimm) on a bounded sample of the workload.
     Returns (records/s median over steps, seconds per step list, sample description, kind)."""
     from slimm_b200 import sldb, synth
@@ -162,6 +162,9 @@ def run_reference_sample(wl, n_sample, steps, warmup, tmp_root=None):
                     times.append(dt)
             sample = (f"{rec.read_id.size} records of the same generator (G={wl['G']}, w={wl['w']}), whole slimm process "
                       f"wall time incl. SAM decode, DB load and bin init, single-threaded binary")
+            if with_cli:
+                CLI_RESULT.clear()
+                CLI_RESULT.update(run_cli_sample(cmd, ref_bin, out, rec.read_id.size, statistics.median(times)))
         else:
             import oracle
             kind = "port"
@@ -178,6 +181,40 @@ def run_reference_sample(wl, n_sample, steps, warmup, tmp_root=None):
         shutil.rmtree(td, ignore_errors=True)
     med = statistics.median(times)
     return rec.read_id.size / med, times, sample, kind
+
+
+CLI_RESULT = {}
+
+
+def run_cli_sample(ref_cmd, ref_bin, out_dir, n_records, ref_seconds):
+    """The drop-in command line (slimm_b200/bin/slimm: threaded SAM decoder -> pinned batches -> the C ABI -> TSV) on the SAME
+    SAM file, database and options the reference binary was just timed on; the decode rate is reported separately."""
+    import re
+    cli = os.path.join(ROOT, "slimm_b200", "bin", "slimm")
+    if not os.path.exists(cli):
+        return {"unavailable": "slimm_b200/bin/slimm not built"}
+    ref_profile = os.path.join(out_dir, "in_profile.tsv")
+    def plain_rows(path):         # rows of taxa proper ("<parent>*" / "0*" rows carry order-dependent f32 sums, DESIGN.md section 4)
+        return sorted(l for l in open(path).read().splitlines() if not l.split("\t")[1:2] or not l.split("\t")[1].endswith("*"))
+    ref_rows = plain_rows(ref_profile) if os.path.exists(ref_profile) else None
+    cmd = [cli, "-v"] + ref_cmd[1:]
+    best, err = None, ""
+    for _ in range(2):            # the first run pays CUDA context creation and page-in of the library
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"unavailable": "slimm_b200/bin/slimm failed: " + r.stderr[-200:]}
+        best, err = dt if best is None else min(best, dt), r.stderr
+    m = re.search(r"decode: (\d+) records, (\d+) reads in ([0-9.e+-]+) s \(([0-9.e+-]+) M records/s, (\d+) host threads\); GPU stages: ([0-9.e+-]+) ms", err)
+    res = {"seconds": best, "records_per_s": n_records / best, "reference_seconds": ref_seconds,
+           "what": "whole process wall time of slimm_b200/bin/slimm on the SAM file of cpu_baseline.sample (process start, CUDA "
+                   "context, .sldb load, threaded SAM decode, pinned uploads, GPU stages, _profile.tsv)"}
+    if m:
+        res.update({"decode_M_records_per_s": float(m.group(4)), "decode_host_threads": int(m.group(5)), "gpu_stages_ms": float(m.group(6))})
+    if ref_rows is not None and os.path.exists(ref_profile):
+        res["profile_rows_equal_to_reference"] = plain_rows(ref_profile) == ref_rows
+    return res
 
 
 def reference_sample_size(wl, budget_s):
@@ -378,7 +415,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rps, times, sample, kind = run_reference_sample(wl, reference_sample_size(wl, 25.0), 1, 0)
+            gpu.close()                   # the command line below creates its own context on this GPU
+            torch.cuda.empty_cache()
+            rps, times, sample, kind = run_reference_sample(wl, reference_sample_size(wl, 25.0), 1, 0, with_cli=True)
             cpu = {"value": rps, "unit": "records/s", "cores": 1, "kind": kind, "sample": sample,
                    "host_cores_available": os.cpu_count()}
         except Exception as e:  # the baseline must never take the GPU number down with it
@@ -389,7 +428,7 @@ def main():
             sys.stderr.write("phases (ms, summed over all resident + e2e steps incl. warm-up): " + json.dumps({k: round(v, 2) for k, v in phases.items()}) + "\n")
         line = dict(base)
         line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": int(launches),
-                     "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                     "roofline": roofline, "cpu_baseline": cpu, "cli": dict(CLI_RESULT) or None, "clocks": clocks,
                      "result": {"hits": summ.hits_count, "reads": summ.matches_count, "uniq": summ.uniq_matches_count,
                                 "uniq2": summ.uniq_matches_count2, "valid_refs": summ.n_valid, "rows": rows,
                                 "pairs": summ.n_pairs, "bins": summ.n_bins, "sorted_input": summ.input_was_sorted}})

@@ -327,9 +327,9 @@ k_coverage(Rec rec, u32 n, CovParams P)
                 const int dist = multi ? (int)lane - win.s : 0;    // records of my read before me
                 const int span = (int)__reduce_max_sync(FULL, (u32)dist);
                 bool rep = false;
-                for (int d = 1; d <= span; ++d) {                  // the same reference earlier in my read?
-                    const u32 t = __shfl_up_sync(FULL, g, d);
-                    rep |= d <= dist && t == g;
+                for (int d = 1; d <= span; d += 2) {               // the same reference earlier in my read?  (two steps per trip)
+                    const u32 t1 = __shfl_up_sync(FULL, g, d), t2 = __shfl_up_sync(FULL, g, d + 1);
+                    rep |= (d <= dist && t1 == g) | (d < dist && t2 == g);
                 }
                 first = multi ? !rep : is_head;
                 const u32 C = __ballot_sync(FULL, multi && first); // the compact stream keeps the distinct references
