@@ -401,7 +401,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
     CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 1) * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
-    const u64 n_tiles = (n_cap + SPLIT_TILE - 1) / SPLIT_TILE;
+    const u64 n_tiles = (n_cap + FINE_TILE - 1) / FINE_TILE;
     if (n_tiles) {
         const int cgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 8));
         k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
