@@ -900,6 +900,22 @@ __device__ __forceinline__ void walk_chunk(const float *buf, u32 c_lo, u32 &i, f
     }
 }
 
+// left fold total + buf[0] + buf[1] + ... (one rounding per addition, in order): the values are loaded sixteen at a time so
+// that the only serial chain is the additions themselves
+__device__ __forceinline__ float fold_in_order(float total, const float *buf, u32 n)
+{
+    u32 k = 0;
+    for (; k + 16 <= n; k += 16) {
+        float x[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) x[t] = buf[k + t];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) total = __fadd_rn(total, x[t]);
+    }
+    for (; k < n; ++k) total = __fadd_rn(total, buf[k]);
+    return total;
+}
+
 // valid set + -v counters (src/slimm.hpp:354-378); one CTA of 1024 threads, after both cut-offs are known
 __device__ __forceinline__ void cutoffs_valid_set(const u32 *__restrict__ stats, u32 G, u32 min_reads, const float *__restrict__ cp_all,
                                                   u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes, DevScalars *sc)
@@ -988,9 +1004,7 @@ k_cutoffs(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, 
             for (u32 k = tid; k < cn; k += 1024) s_buf[k] = __uint_as_float(v[c0 + k]);
             __syncthreads();
             if (tid == 0) {
-                float total = s_f;
-                for (u32 k = 0; k < cn; ++k) total = __fadd_rn(total, s_buf[k]);
-                s_f = total;
+                s_f = fold_in_order(s_f, s_buf, cn);
             }
             __syncthreads();
         }
@@ -1123,24 +1137,21 @@ k_cutoffs_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta,
             const u32 g = g0 + tid;
             const u32 keep = (g < G && stats[4 * g + 3] > 0) ? 1u : 0u;
             const float x = keep ? __ldcg(cp + g) : 0.0f;
-            s_scan[tid] = keep;
+            // rank among the members of this batch of 1024 references: ballot inside the warp, warp totals through shared memory
+            const u32 bal = __ballot_sync(FULL, keep != 0);
+            if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
             __syncthreads();
-            for (u32 d = 1; d < 1024; d <<= 1) {
-                u32 t = tid >= d ? s_scan[tid - d] : 0;
-                __syncthreads();
-                s_scan[tid] += t;
-                __syncthreads();
-            }
-            const u32 base = s_base, tot = s_scan[1023];
+            u32 wbase = 0, tot = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { const u32 t = s_scan[k]; if (k < (int)(tid >> 5)) wbase += t; tot += t; }
+            const u32 base = s_base, pos = wbase + __popc(bal & LANE_LT(tid & 31));
             if (keep) {
-                s_buf[s_scan[tid] - 1] = x;
-                *dsm_key(cl, s_keys, base + s_scan[tid] - 1, share_log) = __float_as_uint(x);
+                s_buf[pos] = x;
+                *dsm_key(cl, s_keys, base + pos, share_log) = __float_as_uint(x);
             }
             __syncthreads();
             if (tid == 0) {
-                float total = s_f;
-                for (u32 k = 0; k < tot; ++k) total = __fadd_rn(total, s_buf[k]);
-                s_f = total;
+                s_f = fold_in_order(s_f, s_buf, tot);
                 s_base = base + tot;
             }
             __syncthreads();
@@ -1457,8 +1468,9 @@ __device__ __forceinline__ u32 lin_neq(const Lin32 &acc)
            ((u32)(acc.b.x != 0) << 4) | ((u32)(acc.b.y != 0) << 5) | ((u32)(acc.b.z != 0) << 6) | ((u32)(acc.b.w != 0) << 7);
 }
 
-template <class Rec, class Lin>
-__global__ void __launch_bounds__(256, ASSIGN_READS_OCC)
+// EXTRA: uniq_cov2 bins / per-read results are wanted (they need the record index of every compact word)
+template <class Rec, class Lin, bool EXTRA>
+__global__ void __launch_bounds__(256, EXTRA ? 4 : ASSIGN_READS_OCC)
 k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
 {
     __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
@@ -1503,7 +1515,7 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict_
             }
             if (ns == 1) {                                         // sole survivor: the read became unique through the filter
                 atomicAdd(P.uniq2_extra + g0, 1u);
-                if (P.cw_idx) {
+                if (EXTRA && P.cw_idx) {
                     const u32 lead = P.cw_idx[(u64)c * CW_SLOT + j0];
                     if (P.cov2) atomicAdd(P.cov2 + bin_of(P.meta, g0, rec.upos(lead), P.half_avg, P.wdiv), 1u);
                     if (P.res_kind) { const u32 hd = P.cw_idx[(u64)c * CW_SLOT + start]; P.res_kind[hd] = 1; P.res_val[hd] = g0; }
@@ -1533,7 +1545,7 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict_
                     for (int d = 0; d < 4; ++d) if (old[d] == 0) *mk[d] = 1u;
                 }
                 count_lca(s_key, s_val, P.lca_cnt, owner * 8 + level);
-                if (P.res_kind) {
+                if (EXTRA && P.res_kind) {
                     const u32 hd = P.cw_idx[(u64)c * CW_SLOT + start];
                     P.res_kind[hd] = 2;
                     P.res_val[hd] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level);

@@ -889,17 +889,22 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
         static const int asg_ctas = getenv("SLIMM_ASG_CTAS") ? atoi(getenv("SLIMM_ASG_CTAS")) : 8;   // CTAs per SM (experiments)
         const int rgrid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * asg_ctas));
         const uint4 *lin32 = (const uint4 *)ctx->d_lin;
+        const bool extra = ctx->d_cw_idx != nullptr || P.res_kind != nullptr;
         if (ctx->use_sorted) {
             const RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
             if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-            else if (ctx->d_lin16) k_assign_reads<RecPacked, Lin16><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else k_assign_reads<RecPacked, Lin32><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            else if (extra && ctx->d_lin16) k_assign_reads<RecPacked, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else if (extra) k_assign_reads<RecPacked, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            else if (ctx->d_lin16) k_assign_reads<RecPacked, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else k_assign_reads<RecPacked, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, (const u32 *)ctx->d_rp_sorted, 2, ctx->d_valid_bits, n);
         } else {
             const RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
             if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-            else if (ctx->d_lin16) k_assign_reads<RecSoA, Lin16><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else k_assign_reads<RecSoA, Lin32><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            else if (extra && ctx->d_lin16) k_assign_reads<RecSoA, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else if (extra) k_assign_reads<RecSoA, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            else if (ctx->d_lin16) k_assign_reads<RecSoA, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else k_assign_reads<RecSoA, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, ctx->d_ref, 1, ctx->d_valid_bits, n);
         }
         ctx->launches += 1 + (P.res_kind ? 1 : 0);
