@@ -158,6 +158,8 @@ int slimm_gpu_p2p_reserve(slimm_gpu_ctx *ctx, uint64_t cap_items, void *ipc_hand
 int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles /* [n_ranks][64] */, uint32_t n_ranks);
 int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts /* [n_ranks][n_slices] */, uint64_t *n_recv);
 int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx);
+/* back to the all-to-all exchange (e.g. when another rank could not map the buffers) */
+int slimm_gpu_p2p_disable(slimm_gpu_ctx *ctx);
 
 /* Stage 2 - reference filter.  Replaces none_zero_bin_count / cov_percent / uniq_cov_percent
  * (src/reference_contig.hpp:84-91,148-155), coverage_cut_off / uniq_coverage_cut_off

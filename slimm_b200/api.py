@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "slimm_profile_rows", "slimm_gpu_set_scatter_mode", "slimm_gpu_set_taxa", "slimm_gpu_profile",
     "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
     "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
-    "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received",
+    "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received", "slimm_gpu_p2p_disable",
 ]
 
 
@@ -126,6 +126,7 @@ def load_library():
     lib.slimm_gpu_p2p_connect.argtypes = [vp, vp, u32]
     lib.slimm_gpu_split_to_peers.argtypes = [vp, vp, C.POINTER(u64)]
     lib.slimm_gpu_accumulate_received.argtypes = [vp]
+    lib.slimm_gpu_p2p_disable.argtypes = [vp]
     lib.slimm_gpu_stats_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     lib.slimm_profile_db_is_tree_consistent.argtypes = [u32, vp, u64, vp, vp, vp, C.POINTER(C.c_int)]
     _lib = lib
@@ -292,6 +293,10 @@ class SlimmGpu:
         n = C.c_uint64(0)
         self._check(self._lib.slimm_gpu_split_to_peers(self._ctx, t.ctypes.data, C.byref(n)), "split_to_peers")
         return int(n.value)
+
+    def p2p_disable(self):
+        self._check(self._lib.slimm_gpu_p2p_disable(self._ctx), "p2p_disable")
+        self.p2p = False
 
     def accumulate_received(self):
         self._check(self._lib.slimm_gpu_accumulate_received(self._ctx), "accumulate_received")

@@ -773,6 +773,14 @@ int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles, uint32_t 
     return SLIMM_GPU_OK;
 }
 
+int slimm_gpu_p2p_disable(slimm_gpu_ctx *ctx)
+{
+    if (!ctx) return SLIMM_GPU_EINVAL;
+    if (ctx->split_pending) return fail(ctx, SLIMM_GPU_ESTATE, "p2p_disable between coverage and split_to_peers");
+    ctx->p2p = false;   // the mappings stay open until destroy; the exchange goes back to slimm_gpu_items_device + accumulate_items
+    return SLIMM_GPU_OK;
+}
+
 int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts, uint64_t *n_recv)
 {
     if (!ctx || !all_counts) return SLIMM_GPU_EINVAL;

@@ -101,7 +101,8 @@ def connect_peers(gpu, device, cap_items: int, group=None) -> bool:
     flag = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     if not int(flag.item()):
-        gpu.p2p = False
+        if getattr(gpu, "p2p", False):
+            gpu.p2p_disable()       # this rank mapped its peers but another one could not: everybody takes the all-to-all
         return False
     return True
 
