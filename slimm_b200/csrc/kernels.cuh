@@ -676,100 +676,118 @@ k_fine_split(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_
     }
 }
 
-// One CTA per fine slice [f_lo + blockIdx.x]: bins in shared memory, items applied with shared atomics, statistics of the
-// references the slice touches (a warp owns 8 consecutive 64-bin steps; a step never straddles two references because
-// the bin offsets are padded to 64), and - when the bins are kept - one coalesced write of the slice.
-__global__ void __launch_bounds__(1024, 1)
+// Persistent CTAs take fine slices from a ticket counter: bins in shared memory, items applied with shared atomics,
+// statistics of the references the slice touches (a warp owns consecutive 64-bin steps; a step never straddles two
+// references because the bin offsets are padded to 64), and - when the bins are kept - one coalesced write of the slice.
+//   PACKED  {cov:16 | uniq_cov:16} in ONE word per bin and one atomic per item.  Exact whenever the slice holds fewer than
+//           65536 items (no counter can reach 2^16) - every slice but the hottest few; 64 KB per CTA, two CTAs per SM, so
+//           one CTA's fill / scan overlaps the other's item loads.  Launched for the slices with fewer than 65536 items;
+//   wide    two u32 per bin (128 KB, one CTA per SM) takes the others (or all of them, SLIMM_GPU_FINE=wide).
+template <bool PACKED, int NT>
+__global__ void __launch_bounds__(NT, PACKED ? 2 : 1)
 k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u32 f_lo, u32 f_hi, u64 Bp, const u64 *__restrict__ off, u32 G,
                   const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
-                  u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket)
+                  u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket,
+                  u32 min_cnt, u32 max_cnt /* this launch takes the slices with min_cnt <= items < max_cnt */)
 {
-    extern __shared__ u32 sh[];                                // cov[FINE_BINS] | uniq_cov[FINE_BINS]
+    extern __shared__ u32 sh[];                                // PACKED: bins[FINE_BINS]; wide: cov[FINE_BINS] | uniq_cov[FINE_BINS]
     __shared__ u32 s_next;
-    u32 *cov = sh, *uq = sh + FINE_BINS;
+    constexpr u32 WORDS = PACKED ? FINE_BINS : 2 * FINE_BINS;
+    constexpr int SPW = 256 / (NT / 32);                       // 64-bin steps per warp
+    constexpr int PRE = PACKED ? 16 : FINE_PRE;                // items per thread requested up front
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 n_steps = Bp >> 6;
-    // persistent CTAs (one per SM: the bins fill its shared memory) take fine slices from a ticket counter
     for (u32 f = f_lo + blockIdx.x; f < f_hi;) {
         if (tid == 0) s_next = f_lo + gridDim.x + atomicAdd(ticket, 1u);   // the next slice's ticket travels while this one is worked on
         const u32 lo = __ldg(start + f), hi = __ldg(start + f + 1);
-        if (lo != hi || hist4) {                               // else: nothing landed here and nobody reads the bins
-            // the first FINE_PRE items per thread are requested first of all: their DRAM latency hides behind the reference
-            // lookup and the zero-fill of the bins
-            const u32 cnt = hi - lo;
-            const u32 *mine = fine + lo + tid;
-            u32 pre[FINE_PRE];
+        const u32 cnt = hi - lo;
+        const bool mine = cnt >= min_cnt && cnt < max_cnt;
+        if (mine && (cnt || hist4)) {                          // an empty slice only matters when somebody reads the bins
+            // the first items of every thread are requested first of all: their DRAM latency hides behind the reference lookup
+            // and the zero-fill of the bins
+            const u32 *my_items = fine + lo + tid;
+            u32 pre[PRE];
 #pragma unroll
-            for (int k = 0; k < FINE_PRE; ++k) pre[k] = (u32)k * 1024 + tid < cnt ? __ldcs(mine + k * 1024) : ITEM_SKIP;
+            for (int k = 0; k < PRE; ++k) pre[k] = (u32)k * NT + tid < cnt ? __ldcs(my_items + k * NT) : ITEM_SKIP;
             const u64 bin0 = (u64)f << FINE_SHIFT;
-            // 256 steps of 64 bins; warp w takes steps 8w .. 8w+7.  Its first reference is looked up now (among the few
-            // references the slice touches), so that the dependent loads are long done when the bins are complete.
-            const u64 step0 = (bin0 >> 6) + wid * 8;
-            const u32 my_steps = step0 >= n_steps ? 0u : (u32)min((u64)8, n_steps - step0);
+            // my SPW steps; the first reference is looked up now, among the few references the slice touches
+            const u64 step0 = (bin0 >> 6) + wid * SPW;
+            const u32 my_steps = step0 >= n_steps ? 0u : (u32)min((u64)SPW, n_steps - step0);
             u32 g = 0;
             u64 g_end = 0;
-            if (lo != hi && my_steps) {
+            if (cnt && my_steps) {
                 u32 a = __ldg(fine_ref + f), b = min(__ldg(fine_ref + f + 1) + 1u, G);   // largest g in [a, b) with off[g] <= my first bin
                 const u64 first_bin = step0 << 6;
                 while (b - a > 1) { const u32 mid = (a + b) >> 1; if (__ldg(off + mid) <= first_bin) a = mid; else b = mid; }
                 g = a;
                 g_end = __ldg(off + g + 1);
             }
-            for (u32 k = tid; k < 2 * FINE_BINS / 4; k += 1024) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
+            for (u32 k = tid; k < WORDS / 4; k += NT) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < FINE_PRE; ++k)
+            for (int k = 0; k < PRE; ++k)
                 if (pre[k] != ITEM_SKIP) {
                     const u32 b = pre[k] & (FINE_BINS - 1);
-                    atomicAdd(&cov[b], 1u);
-                    if (pre[k] >> 31) atomicAdd(&uq[b], 1u);
+                    if (PACKED) atomicAdd(&sh[b], (pre[k] >> 31) ? 0x10001u : 1u);
+                    else { atomicAdd(&sh[b], 1u); if (pre[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u); }
                 }
-            for (u32 i0 = FINE_PRE * 1024; i0 < cnt; i0 += 4 * 1024) {     // a slice with more items than usual
+            for (u32 i0 = PRE * NT; i0 < cnt; i0 += 4 * NT) {      // a slice with more items than usual
                 u32 v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = i0 + k * 1024 + tid < cnt ? __ldcs(mine + i0 + k * 1024) : ITEM_SKIP;
+                for (int k = 0; k < 4; ++k) v[k] = i0 + k * NT + tid < cnt ? __ldcs(my_items + i0 + k * NT) : ITEM_SKIP;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (v[k] != ITEM_SKIP) {
                         const u32 b = v[k] & (FINE_BINS - 1);
-                        atomicAdd(&cov[b], 1u);
-                        if (v[k] >> 31) atomicAdd(&uq[b], 1u);
+                        if (PACKED) atomicAdd(&sh[b], (v[k] >> 31) ? 0x10001u : 1u);
+                        else { atomicAdd(&sh[b], 1u); if (v[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u); }
                     }
             }
             __syncthreads();
             if (my_steps) {
-                // my 8 steps: bins [wid * 512, wid * 512 + 512) of the slice, lane l holds bins 2l, 2l+1 of every step
-                const u32 wb = wid * 512 + 2 * lane;
-                uint4 v[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const uint2 c2 = *reinterpret_cast<const uint2 *>(cov + wb + t * 64), u2 = *reinterpret_cast<const uint2 *>(uq + wb + t * 64);
-                    v[t] = make_uint4(c2.x, u2.x, c2.y, u2.y);
-                }
-                if (hist4) {
-                    uint4 *dst = hist4 + step0 * 32 + lane;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) if ((u32)t < my_steps) __stcs(dst + t * 32, v[t]);
-                }
-                if (lo != hi) {
-                    u32 nz = 0, sum = 0, unz = 0, usum = 0;
-                    const u64 first_bin = step0 << 6;
+                // bins [wid * SPW * 64, (wid + 1) * SPW * 64) of the slice, eight steps at a time; lane l holds bins 2l, 2l+1 of a step
+                u32 nz = 0, sum = 0, unz = 0, usum = 0;
+#pragma unroll 1
+                for (int h = 0; h < SPW / 8; ++h) {
+                    const u32 wb = (wid * SPW + h * 8) * 64 + 2 * lane;
+                    uint4 v[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        if ((u32)t < my_steps) {
-                            if (first_bin + (u64)t * 64 >= g_end) {        // warp-uniform: the step starts another reference
-                                nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
-                                if (lane == 0 && (nz | unz)) {
-                                    atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
-                                    if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
-                                }
-                                nz = sum = unz = usum = 0;
-                                while (first_bin + (u64)t * 64 >= g_end) { ++g; g_end = __ldg(off + g + 1); }
-                            }
-                            nz += (v[t].x != 0) + (v[t].z != 0); sum += v[t].x + v[t].z;
-                            unz += (v[t].y != 0) + (v[t].w != 0); usum += v[t].y + v[t].w;
+                        if (PACKED) {
+                            const uint2 w2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64);
+                            v[t] = make_uint4(w2.x & 0xFFFFu, w2.x >> 16, w2.y & 0xFFFFu, w2.y >> 16);
+                        } else {
+                            const uint2 c2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64),
+                                        u2 = *reinterpret_cast<const uint2 *>(sh + FINE_BINS + wb + t * 64);
+                            v[t] = make_uint4(c2.x, u2.x, c2.y, u2.y);
                         }
                     }
+                    if (hist4) {
+                        uint4 *dst = hist4 + (step0 + h * 8) * 32 + lane;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) if ((u32)(h * 8 + t) < my_steps) __stcs(dst + t * 32, v[t]);
+                    }
+                    if (cnt) {
+                        const u64 first_bin = (step0 + h * 8) << 6;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            if ((u32)(h * 8 + t) < my_steps) {
+                                if (first_bin + (u64)t * 64 >= g_end) {    // warp-uniform: the step starts another reference
+                                    nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
+                                    if (lane == 0 && (nz | unz)) {
+                                        atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);
+                                        if (unz) { atomicAdd(stats + 4 * g + 2, unz); atomicAdd(stats + 4 * g + 3, usum); }
+                                    }
+                                    nz = sum = unz = usum = 0;
+                                    while (first_bin + (u64)t * 64 >= g_end) { ++g; g_end = __ldg(off + g + 1); }
+                                }
+                                nz += (v[t].x != 0) + (v[t].z != 0); sum += v[t].x + v[t].z;
+                                unz += (v[t].y != 0) + (v[t].w != 0); usum += v[t].y + v[t].w;
+                            }
+                        }
+                    }
+                }
+                if (cnt) {
                     nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
                     if (lane == 0 && (nz | unz)) {
                         atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);

@@ -81,6 +81,7 @@ struct slimm_gpu_ctx {
     // fine slices: the histogram is accumulated in shared memory, 2^14 bins per CTA (k_fine_*)
     u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
     int acc_mode = 1;                       // 1: fine slices in shared memory, 0: 64-bit REDs into L2-resident slices
+    bool fine_packed = true;                // slices with fewer than 65536 items use 16+16-bit counters (64 KB per CTA)
     bool stats_done = false;                // the accumulate stage already reduced the per-reference statistics
     bool shard_acc_done = false;
     int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
@@ -244,7 +245,9 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
     if (const char *e = getenv("SLIMM_GPU_ACC")) ctx->acc_mode = !strcmp(e, "l2") ? 0 : 1;
     if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "SLIMM_GPU_SKIP_BINS and SLIMM_GPU_KEEP_UNIQ_COV2 exclude each other");
-    CU(cudaFuncSetAttribute(k_fine_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
+    if (const char *e = getenv("SLIMM_GPU_FINE")) ctx->fine_packed = strcmp(e, "wide") != 0;
     if (const char *e = getenv("SLIMM_GPU_ASSIGN")) ctx->assign_variant = !strcmp(e, "window") ? 0 : 1;
     if (G < 65536) {
         // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
@@ -394,12 +397,12 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     if (ctx->fine_slices_cap < n_fine) {
         cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor);
         ctx->d_fine_cnt = ctx->d_fine_start = ctx->d_fine_cursor = nullptr; ctx->fine_slices_cap = 0;
-        CU(cudaMalloc(&ctx->d_fine_cnt, (n_fine + 1) * 4)); CU(cudaMalloc(&ctx->d_fine_start, (n_fine + 1) * 4));
+        CU(cudaMalloc(&ctx->d_fine_cnt, (n_fine + 2) * 4)); CU(cudaMalloc(&ctx->d_fine_start, (n_fine + 1) * 4));
         CU(cudaMalloc(&ctx->d_fine_cursor, (n_fine + 1) * 4));
         ctx->fine_slices_cap = n_fine;
     }
     TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
-    CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 1) * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 2) * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
     const u64 n_tiles = (n_cap + FINE_TILE - 1) / FINE_TILE;
     if (n_tiles) {
@@ -414,10 +417,21 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
         uint4 *hist4 = (ctx->flags & SLIMM_GPU_SKIP_BINS) ? nullptr : (uint4 *)ctx->d_hist;
-        u32 *ticket = ctx->d_fine_cnt + n_fine;                // spare word behind the counts (zeroed with them)
-        const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
-        k_fine_accumulate<<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off, ctx->G,
-                                                                         ctx->d_fine_ref, ctx->d_stats, hist4, ticket);
+        u32 *ticket = ctx->d_fine_cnt + n_fine;                // two spare words behind the counts (zeroed with them)
+        if (ctx->fine_packed) {
+            // slices with fewer than 65536 items (all but the hottest): packed counters, two CTAs per SM; then the rest, wide
+            const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * 2);
+            k_fine_accumulate<true, 512><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u);
+            const unsigned grid1 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
+            k_fine_accumulate<false, 1024><<<grid1, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket + 1, 65536u, 0xFFFFFFFFu);
+            ctx->launches++;
+        } else {
+            const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
+            k_fine_accumulate<false, 1024><<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu);
+        }
     }
     ctx->launches += 4;
     CU(cudaGetLastError());

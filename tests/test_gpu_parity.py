@@ -217,7 +217,7 @@ def test_alternative_paths_agree(env, value, monkeypatch):
     assert len(out[0]) > 10
 
 
-@pytest.mark.parametrize("env,value", [("SLIMM_GPU_ACC", "l2"), ("SLIMM_GPU_ASSIGN", "window")])
+@pytest.mark.parametrize("env,value", [("SLIMM_GPU_ACC", "l2"), ("SLIMM_GPU_ASSIGN", "window"), ("SLIMM_GPU_FINE", "wide")])
 def test_alternative_kernels_agree(env, value, monkeypatch):
     """The older kernels stay selectable for A/B runs (64-bit REDs into L2-resident slices instead of the shared-memory
     fine slices; sliding-window assign instead of one thread per read): same results, bins included."""
@@ -261,3 +261,37 @@ def test_skip_bins_profile_only_run():
                 gpu.fetch_bins(0, 0)
     with pytest.raises(api.SlimmGpuError):
         api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.SKIP_BINS | api.KEEP_UNIQ_COV2)
+
+
+def test_hot_fine_slice():
+    """All records in one fine slice (a few short references): more than 65535 items per slice, so the packed 16+16-bit
+    counters do not apply and the wide shared-memory variant runs; bins included."""
+    contigs, rec, lineage = _synthetic(4, 400_000, 8, len_lo=2000, len_hi=5000, multi_frac=0.5, k_lo=2, k_hi=3, neigh=2)
+    w = 5
+    res = oracle.run(contigs.lengths, lineage, w, 100, 0.95, rec.read_id, rec.ref_id, rec.begin_pos)
+    assert res.n_pairs > 65536 and int(res.bin_off[-1]) < 16384
+    with api.SlimmGpu(contigs.lengths, lineage, w, 100) as gpu:
+        gpu.set_scatter_mode(1)
+        gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
+        gpu.run(0.95)
+        st = gpu.ref_stats()
+        for x, y in ((st.reads_count, res.reads_count), (st.uniq_reads_count, res.uniq_reads_count), (st.nz_bins, res.nz),
+                     (st.uniq_nz_bins, res.unz), (st.uniq_reads_count2, res.uniq_reads_count2), (st.valid, res.valid)):
+            np.testing.assert_array_equal(x, y)
+        for g in range(4):
+            a, b = int(res.bin_off[g]), int(res.bin_off[g + 1])
+            np.testing.assert_array_equal(gpu.fetch_bins(0, g), res.cov[a:b])
+            np.testing.assert_array_equal(gpu.fetch_bins(1, g), res.uniq_cov[a:b])
+    # one bin hit by 100 000 unique reads: a counter beyond 16 bits
+    n = 100_000
+    rid = np.arange(n, dtype=np.uint32); ref = np.zeros(n, dtype=np.uint32); pos = np.full(n, 100, dtype=np.int32)
+    res = oracle.run(contigs.lengths, lineage, w, 100, 0.95, rid, ref, pos)
+    assert int(res.cov.max()) == n
+    with api.SlimmGpu(contigs.lengths, lineage, w, 100) as gpu:
+        gpu.set_scatter_mode(1)
+        gpu.push(rid, ref, pos)
+        gpu.run(0.95)
+        a, b = int(res.bin_off[0]), int(res.bin_off[1])
+        np.testing.assert_array_equal(gpu.fetch_bins(0, 0), res.cov[a:b])
+        np.testing.assert_array_equal(gpu.fetch_bins(1, 0), res.uniq_cov[a:b])
+        np.testing.assert_array_equal(gpu.ref_stats().reads_count, res.reads_count)
