@@ -574,8 +574,9 @@ k_fine_count(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_
 }
 
 // start[f] = cursor[f] = items before fine slice f; start[n_fine] = all items.  One block.
+// Also lists the HOT slices (65536 items or more: the ones the packed accumulate leaves to the wide one) in hot[0 .. *n_hot).
 __global__ void __launch_bounds__(1024)
-k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor)
+k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor, u32 *__restrict__ hot, u32 *__restrict__ n_hot)
 {
     __shared__ u32 s_warp[32];
     __shared__ u32 s_run;
@@ -594,7 +595,11 @@ k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u3
 #pragma unroll
         for (int k = 0; k < 32; ++k) { const u32 t = s_warp[k]; if (k < (int)wid) wbase += t; all += t; }
         const u32 run = s_run;
-        if (f < n_fine) { const u32 e = run + wbase + x - v; start[f] = e; cursor[f] = e; }
+        if (f < n_fine) {
+            const u32 e = run + wbase + x - v;
+            start[f] = e; cursor[f] = e;
+            if (v >= 65536u) hot[atomicAdd(n_hot, 1u)] = f;    // at most 2^16 of them (fewer than 2^32 items)
+        }
         __syncthreads();
         if (tid == 0) s_run = run + all;
         __syncthreads();
@@ -688,7 +693,8 @@ __global__ void __launch_bounds__(NT, PACKED ? 2 : 1)
 k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u32 f_lo, u32 f_hi, u64 Bp, const u64 *__restrict__ off, u32 G,
                   const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
                   u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket,
-                  u32 min_cnt, u32 max_cnt /* this launch takes the slices with min_cnt <= items < max_cnt */)
+                  u32 min_cnt, u32 max_cnt /* this launch takes the slices with min_cnt <= items < max_cnt */,
+                  const u32 *__restrict__ hot, const u32 *__restrict__ n_hot /* not null: walk this list of slices instead of all of them */)
 {
     extern __shared__ u32 sh[];                                // PACKED: bins[FINE_BINS]; wide: cov[FINE_BINS] | uniq_cov[FINE_BINS]
     __shared__ u32 s_next;
@@ -697,8 +703,10 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
     constexpr int PRE = PACKED ? 16 : FINE_PRE;                // items per thread requested up front
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 n_steps = Bp >> 6;
-    for (u32 f = f_lo + blockIdx.x; f < f_hi;) {
-        if (tid == 0) s_next = f_lo + gridDim.x + atomicAdd(ticket, 1u);   // the next slice's ticket travels while this one is worked on
+    const u32 n_list = hot ? *n_hot : 0u;
+    u32 idx = blockIdx.x;                                      // list mode: my position in the list
+    for (u32 f = hot ? (idx < n_list ? hot[idx] : f_hi) : f_lo + blockIdx.x; f < f_hi;) {
+        if (!hot && tid == 0) s_next = f_lo + gridDim.x + atomicAdd(ticket, 1u);   // the next slice's ticket travels while this one is worked on
         const u32 lo = __ldg(start + f), hi = __ldg(start + f + 1);
         const u32 cnt = hi - lo;
         const bool mine = cnt >= min_cnt && cnt < max_cnt;
@@ -797,7 +805,8 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
             }
         }
         __syncthreads();                                       // everybody is done with the bins; s_next is visible
-        f = s_next;
+        if (hot) { idx += gridDim.x; f = idx < n_list ? hot[idx] : f_hi; }
+        else f = s_next;
         __syncthreads();
     }
 }

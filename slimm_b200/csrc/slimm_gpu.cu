@@ -79,7 +79,7 @@ struct slimm_gpu_ctx {
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
     u32 **d_dest = nullptr;
     // fine slices: the histogram is accumulated in shared memory, 2^14 bins per CTA (k_fine_*)
-    u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
+    u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr, *d_fine_hot = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
     int acc_mode = 1;                       // 1: fine slices in shared memory, 0: 64-bit REDs into L2-resident slices
     bool fine_packed = true;                // slices with fewer than 65536 items use 16+16-bit counters (64 KB per CTA)
     bool stats_done = false;                // the accumulate stage already reduced the per-reference statistics
@@ -293,7 +293,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest);
-    cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref);
+    cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref); cudaFree(ctx->d_fine_hot);
     for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
     cudaFree(ctx->d_recv);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
@@ -401,6 +401,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
         CU(cudaMalloc(&ctx->d_fine_cursor, (n_fine + 1) * 4));
         ctx->fine_slices_cap = n_fine;
     }
+    if (!ctx->d_fine_hot) CU(cudaMalloc(&ctx->d_fine_hot, 65536 * 4));   // slices with >= 65536 items: fewer than 2^16 of them
     TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
     CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 2) * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
@@ -409,7 +410,8 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
         const int cgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 8));
         k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
     }
-    k_fine_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor);
+    k_fine_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot,
+                                             ctx->d_fine_cnt + n_fine + 1);
     if (n_tiles) {
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
         k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
@@ -417,20 +419,20 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
         uint4 *hist4 = (ctx->flags & SLIMM_GPU_SKIP_BINS) ? nullptr : (uint4 *)ctx->d_hist;
-        u32 *ticket = ctx->d_fine_cnt + n_fine;                // two spare words behind the counts (zeroed with them)
+        u32 *ticket = ctx->d_fine_cnt + n_fine;                // two spare words behind the counts (zeroed with them): ticket, number of hot slices
         if (ctx->fine_packed) {
             // slices with fewer than 65536 items (all but the hottest): packed counters, two CTAs per SM; then the rest, wide
             const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * 2);
             k_fine_accumulate<true, 512><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u);
+                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr);
             const unsigned grid1 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
             k_fine_accumulate<false, 1024><<<grid1, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket + 1, 65536u, 0xFFFFFFFFu);
+                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 65536u, 0xFFFFFFFFu, ctx->d_fine_hot, ticket + 1);   // walks the list of hot slices k_fine_scan left
             ctx->launches++;
         } else {
             const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
             k_fine_accumulate<false, 1024><<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu);
+                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu, nullptr, nullptr);
         }
     }
     ctx->launches += 4;
