@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -103,9 +104,14 @@ struct ParsedChunk {
     std::vector<uint32_t> key_off, key_len, ref;
     std::vector<int32_t> pos;
     std::vector<char> keys;          // read keys back to back
+    std::vector<uint8_t> new_run;    // grouped-input fast path: record i >= 1 starts another read than record i - 1
     uint64_t n_records = 0;          // records seen, kept or not
     std::string error;
-    void clear() { hash.clear(); key_off.clear(); key_len.clear(); ref.clear(); pos.clear(); keys.clear(); n_records = 0; error.clear(); }
+    void clear() { hash.clear(); key_off.clear(); key_len.clear(); ref.clear(); pos.clear(); keys.clear(); new_run.clear(); n_records = 0; error.clear(); }
+    bool same_key(size_t i, size_t j) const
+    {
+        return hash[i] == hash[j] && key_len[i] == key_len[j] && memcmp(keys.data() + key_off[i], keys.data() + key_off[j], key_len[i]) == 0;
+    }
     size_t size() const { return hash.size(); }
     void add(const char *name, size_t name_len, uint32_t flag, uint32_t rid, int32_t begin_pos)
     {
@@ -281,6 +287,50 @@ private:
     std::vector<uint32_t> key_len_;
 };
 
+// ---- grouped-input fast path ----------------------------------------------------------------------
+// Mapper output is grouped by read: every read name forms ONE run of consecutive records.  Then the dense id of a
+// record is simply the number of runs before it, and the serial name -> id table is not needed at all - provided no
+// name ever starts a second run.  The parse workers check exactly that, in parallel: every run head's 64-bit key hash
+// goes into this sharded set; a hash seen twice (a name that comes back, or a 2^-64 collision) clears `grouped` and
+// the caller decodes again through the exact table.  Both paths give identical ids whenever the fast one applies.
+class RunHeadSet {
+public:
+    RunHeadSet() : shards_(N_SHARDS) {}
+    // true when h was already there
+    bool insert(uint64_t h)
+    {
+        if (h == 0) h = 0x9E3779B97F4A7C15ull;                // 0 marks an empty slot
+        Shard &sh = shards_[h >> (64 - SHARD_BITS)];
+        std::lock_guard<std::mutex> lk(sh.m);
+        if (sh.slots.empty()) { sh.slots.assign(1u << 10, 0); }
+        size_t mask = sh.slots.size() - 1, s = (h * 0xD6E8FEB86659FD93ull >> 20) & mask;
+        while (sh.slots[s]) {
+            if (sh.slots[s] == h) return true;
+            s = (s + 1) & mask;
+        }
+        sh.slots[s] = h;
+        if (++sh.n * 10 > sh.slots.size() * 6) {
+            std::vector<uint64_t> old;
+            old.swap(sh.slots);
+            sh.slots.assign(old.size() * 2, 0);
+            mask = sh.slots.size() - 1;
+            for (uint64_t v : old)
+                if (v) {
+                    size_t t = (v * 0xD6E8FEB86659FD93ull >> 20) & mask;
+                    while (sh.slots[t]) t = (t + 1) & mask;
+                    sh.slots[t] = v;
+                }
+        }
+        return false;
+    }
+
+private:
+    static const int SHARD_BITS = 10;
+    static const size_t N_SHARDS = 1u << SHARD_BITS;
+    struct Shard { std::mutex m; std::vector<uint64_t> slots; size_t n = 0; };
+    std::vector<Shard> shards_;
+};
+
 // ---- the decoder --------------------------------------------------------------------------------
 struct RecordBatch {
     uint32_t *read_id = nullptr, *ref_id = nullptr;
@@ -291,6 +341,7 @@ struct RecordBatch {
 struct DecodeStats {
     uint64_t records_in_file = 0, records_kept = 0, reads = 0;
     double seconds = 0.0;
+    bool not_grouped = false;        // grouped-input fast path only: a read name came back after its run had ended - decode again, exact
 };
 
 class AlignmentDecoder {
@@ -347,14 +398,20 @@ public:
 
     // Decodes the whole file.  sink(batch) is called on the calling thread with every filled batch (and the last,
     // partial one); it returns the batch to fill next (double buffering is the sink's business).
+    // assume_grouped: dense ids by counting runs of equal names, verified in parallel (RunHeadSet).  When the file
+    // turns out not to be grouped by read the call stops early with st.not_grouped set (and returns false with an
+    // empty err): the caller discards what the sink received and calls decode again with assume_grouped = false.
     template <class Sink>
-    bool decode(int n_threads, RecordBatch first, Sink &&sink, DecodeStats &st, std::string &err)
+    bool decode(int n_threads, RecordBatch first, Sink &&sink, DecodeStats &st, std::string &err, bool assume_grouped = false)
     {
+        st = DecodeStats();
+        RunHeadSet heads;
+        std::atomic<bool> came_back(false);
         n_threads = std::max(1, n_threads);
         const int n_parse = std::max(1, comp_ == Compression::bgzf ? n_threads / 2 : n_threads - 1);
         const int n_inflate = std::max(1, n_threads - n_parse);
         const uint32_t n_refs = (uint32_t)header_.names.size();
-        OrderedStage<ParseJob, ParsedChunk> parse(n_parse, (size_t)n_parse * 3 + 2, [this, n_refs](ParseJob &job, ParsedChunk &out) {
+        OrderedStage<ParseJob, ParsedChunk> parse(n_parse, (size_t)n_parse * 3 + 2, [this, n_refs, assume_grouped, &heads, &came_back](ParseJob &job, ParsedChunk &out) {
             const size_t guess = (job.end - job.begin) / (is_bam_ ? 200 : 250) + 16;
             out.hash.reserve(guess); out.key_off.reserve(guess); out.key_len.reserve(guess); out.ref.reserve(guess); out.pos.reserve(guess);
             out.keys.reserve(guess * 24);
@@ -365,6 +422,15 @@ public:
             if (out.error.empty() && job.buf) {
                 if (is_bam_) parse_bam_range(job.buf->p + job.begin, job.buf->p + job.end, n_refs, out);
                 else parse_sam_range(job.buf->p + job.begin, job.buf->p + job.end, names_, out);
+            }
+            if (assume_grouped && out.error.empty()) {        // run heads inside the chunk; record 0 is the consumer's business
+                const size_t n = out.size();
+                out.new_run.assign(n, 0);
+                for (size_t i = 1; i < n; ++i)
+                    if (!out.same_key(i, i - 1)) {
+                        out.new_run[i] = 1;
+                        if (heads.insert(out.hash[i])) came_back.store(true, std::memory_order_relaxed);
+                    }
             }
         });
         std::string frame_err;
@@ -381,10 +447,36 @@ public:
         bool have_prev = false;
         ParsedChunk ch;
         bool ok = true;
+        uint64_t next_id = 0;                                 // grouped fast path: runs seen so far
         while (parse.pop(ch)) {
             if (!ch.error.empty()) { err = ch.error; ok = false; break; }
             st.records_in_file += ch.n_records;
             const size_t n = ch.size();
+            if (assume_grouped) {
+                if (came_back.load(std::memory_order_relaxed)) { st.not_grouped = true; ok = false; break; }
+                for (size_t i = 0; i < n; ++i) {
+                    bool fresh;
+                    if (i) fresh = ch.new_run[i] != 0;
+                    else {                                     // does the chunk continue the previous chunk's last read?
+                        const char *key = ch.keys.data() + ch.key_off[0];
+                        fresh = !(have_prev && ch.hash[0] == prev_hash && prev_key.size() == ch.key_len[0] && memcmp(prev_key.data(), key, ch.key_len[0]) == 0);
+                        if (fresh && heads.insert(ch.hash[0])) came_back.store(true, std::memory_order_relaxed);
+                    }
+                    if (fresh) {
+                        if (next_id >= 0xFFFFFFFEull) { err = "more than 2^32-2 distinct reads"; ok = false; break; }
+                        ++next_id;
+                    }
+                    if (batch.n == batch.cap) { batch = sink(batch); batch.n = 0; }
+                    batch.read_id[batch.n] = (uint32_t)(next_id - 1); batch.ref_id[batch.n] = ch.ref[i]; batch.begin_pos[batch.n] = ch.pos[i];
+                    ++batch.n;
+                }
+                if (!ok) break;
+                if (n) {
+                    prev_key.assign(ch.keys.data() + ch.key_off[n - 1], ch.key_len[n - 1]); prev_hash = ch.hash[n - 1]; have_prev = true;
+                }
+                st.records_kept += n;
+                continue;
+            }
             for (size_t i = 0; i < n; ++i) {
                 if (i + 8 < n) table.prefetch(ch.hash[i + 8]);
                 const char *key = ch.keys.data() + ch.key_off[i];
@@ -403,11 +495,12 @@ public:
             if (!ok) break;
             st.records_kept += n;
         }
+        if (ok && assume_grouped && came_back.load()) { st.not_grouped = true; ok = false; }   // every worker is done by now
         if (!ok) parse.abort();
         framer.join();
         if (ok && !frame_err.empty()) { err = frame_err; ok = false; }
         if (ok && batch.n) sink(batch);
-        st.reads = table.size();
+        st.reads = assume_grouped ? next_id : table.size();
         return ok;
     }
 

@@ -42,6 +42,7 @@ struct Options {
     std::string rank = "species", input_path, output_prefix, database_path;
     // extras of this front end (not in the reference)
     std::string dump_records;        // --dump-records FILE: decode only, write the SoA (test hook, needs no GPU)
+    bool exact_ids = false;          // --exact-ids: always assign read ids through the name table (skip the grouped-input fast path)
     int threads = 0, device = 0;
 };
 
@@ -112,7 +113,8 @@ static void print_help()
                  "    -ro, --raw-output             Output raw reference statstics\n"
                  "    -co, --coverage-output        Output raw coverage statstics\n"
                  "    -v, --verbose                 Enable verbose output.\n"
-                 "    --threads INT                 host decode threads (default: all cores); --device INT  CUDA device (default 0)\n";
+                 "    --threads INT                 host decode threads (default: all cores); --device INT  CUDA device (default 0)\n"
+                 "    --exact-ids                   always assign read ids through the read-name table (skip the grouped-input fast path)\n";
 }
 
 static bool parse_number(const std::string &s, double &v)
@@ -171,6 +173,7 @@ static int parse_command_line(int argc, char **argv, Options &o)
             else if (a == "--threads") { if (!value(s)) return 1; o.threads = atoi(s.c_str()); }
             else if (a == "--device") { if (!value(s)) return 1; o.device = atoi(s.c_str()); }
             else if (a == "--dump-records") { if (!value(o.dump_records)) return 1; }
+            else if (a == "--exact-ids") o.exact_ids = true;
             else { std::cerr << "slimm: illegal option -- " << a << "\n"; return 1; }
         } else pos.push_back(a);
     }
@@ -234,11 +237,17 @@ static bool dump_records_file(const Options &opt, AlignmentDecoder &dec, uint32_
     RecordBatch batch{b_rid.data(), b_ref.data(), b_pos.data(), 0, cap};
     DecodeStats st;
     std::string err;
-    const bool ok = dec.decode(threads, batch, [&](RecordBatch b) {
-        rid.insert(rid.end(), b.read_id, b.read_id + b.n); ref.insert(ref.end(), b.ref_id, b.ref_id + b.n);
-        pos.insert(pos.end(), b.begin_pos, b.begin_pos + b.n);
-        return b;
-    }, st, err);
+    bool ok = false;
+    for (int attempt = (opt.exact_ids || threads < 3) ? 1 : 0; attempt < 2; ++attempt) {   // grouped-input fast path first (it needs parse workers to pay off), the exact name table if a read comes back
+        rid.clear(); ref.clear(); pos.clear();
+        batch.n = 0;
+        ok = dec.decode(threads, batch, [&](RecordBatch b) {
+            rid.insert(rid.end(), b.read_id, b.read_id + b.n); ref.insert(ref.end(), b.ref_id, b.ref_id + b.n);
+            pos.insert(pos.end(), b.begin_pos, b.begin_pos + b.n);
+            return b;
+        }, st, err, attempt == 0);
+        if (ok || !st.not_grouped) break;
+    }
     if (!ok) { std::cerr << "slimm: " << err << "\n"; return false; }
     std::ofstream f(opt.dump_records, std::ios::binary);
     const uint64_t G = dec.header().names.size(), N = rid.size();
@@ -431,13 +440,25 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
         uint64_t pushed = 0;
         DecodeStats st;
         Timer dt;
-        const bool dec_ok = dec.decode(threads, batches[0], [&](RecordBatch b) {
-            check(slimm_gpu_push(ctx, b.read_id, b.ref_id, b.begin_pos, b.n), ctx, "slimm_gpu_push");
-            pushed += b.n;
-            cur = (cur + 1) % NB;
-            if (pushed >= (uint64_t)(NB - 1) * cap) check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");   // the buffer about to be refilled is free again
-            return batches[cur];
-        }, st, err);
+        bool dec_ok = false;
+        // Mapper output is grouped by read: ids by counting runs, checked in parallel by the parse workers.  If a read name
+        // comes back after its run has ended (coordinate-sorted input), what was pushed is dropped and the file is decoded
+        // again through the exact name table.
+        for (int attempt = (opt.exact_ids || threads < 3) ? 1 : 0; attempt < 2; ++attempt) {
+            cur = 0; pushed = 0;
+            batches[0].n = 0;
+            dec_ok = dec.decode(threads, batches[0], [&](RecordBatch b) {
+                check(slimm_gpu_push(ctx, b.read_id, b.ref_id, b.begin_pos, b.n), ctx, "slimm_gpu_push");
+                pushed += b.n;
+                cur = (cur + 1) % NB;
+                if (pushed >= (uint64_t)(NB - 1) * cap) check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");   // the buffer about to be refilled is free again
+                return batches[cur];
+            }, st, err, attempt == 0);
+            if (dec_ok || !st.not_grouped) break;
+            check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");
+            check(slimm_gpu_reset(ctx, 0, 0), ctx, "slimm_gpu_reset");
+            if (opt.verbose) std::cerr << "\n  (input is not grouped by read: decoding again with the exact read-name table) ";
+        }
         if (!dec_ok) throw GpuError{SLIMM_GPU_EINVAL, input + ": " + err};
         check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");
         const double dsec = dt.elapsed();

@@ -24,9 +24,9 @@ def _built():
     assert os.path.exists(CLI)
 
 
-def decode(path, tmp_path, threads=4):
+def decode(path, tmp_path, threads=4, extra=()):
     out = str(tmp_path / "dump.bin")
-    r = subprocess.run([CLI, "--threads", str(threads), "--dump-records", out, "none.sldb", str(path)], capture_output=True, text=True)
+    r = subprocess.run([CLI, "--threads", str(threads), "--dump-records", out, *extra, "none.sldb", str(path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return sf.load_dump(out)
 
@@ -100,6 +100,28 @@ def test_decoder_formats_and_chunk_boundaries(fmt, shuffle, tmp_path):
         d = decode(p, tmp_path, threads)
         assert_records(d, rec, names, lengths, 100)
         assert d["n_records"] == len(fx.qname) and d["n_reads"] == rec.n_reads
+
+
+@pytest.mark.parametrize("fmt", ["sam", "bam"])
+def test_grouped_input_fast_path_gives_the_table_ids(fmt, tmp_path):
+    """Input grouped by read (what mappers write): ids by counting runs, verified in parallel by the parse workers, are the
+    ids of the exact read-name table; a name that comes back makes the decoder fall back to that table (same ids again)."""
+    names, lengths, fx = _fixture(70_000, 13)
+    assert fx.qname[-1] == "frag3"
+    for grouped in (True, False):
+        q, fl, rf, ps = (fx.qname[:-1], fx.flag[:-1], fx.ref_id[:-1], fx.pos1[:-1]) if grouped else (fx.qname, fx.flag, fx.ref_id, fx.pos1)
+        rec = synth.records_from_sam_fixture(synth.SamFixture(list(q), np.asarray(fl), np.asarray(rf), np.asarray(ps)))
+        if fmt == "bam":
+            p = tmp_path / "in.bam"
+            p.write_bytes(sf.bgzf_compress(sf.bam_bytes(names, lengths, q, fl, rf, ps), level=1))
+        else:
+            p = tmp_path / "in.sam"
+            p.write_bytes(sf.sam_text(names, lengths, q, fl, rf, ps).encode())
+        fast = decode(p, tmp_path, 6)
+        exact = decode(p, tmp_path, 6, extra=("--exact-ids",))
+        for d in (fast, exact):
+            assert_records(d, rec, names, lengths, 100)
+            assert d["n_records"] == len(q) and d["n_reads"] == rec.n_reads
 
 
 def test_avg_read_length_uses_first_records_with_seq(tmp_path):
