@@ -299,9 +299,40 @@ public:
     // true when h was already there
     bool insert(uint64_t h)
     {
-        if (h == 0) h = 0x9E3779B97F4A7C15ull;                // 0 marks an empty slot
+        if (h == 0) h = EMPTY_ALIAS;
         Shard &sh = shards_[h >> (64 - SHARD_BITS)];
         std::lock_guard<std::mutex> lk(sh.m);
+        return insert_locked(sh, h);
+    }
+    // A chunk's run heads at once: grouped by shard first, so that a shard is locked once per chunk and its small table
+    // stays in cache while the chunk's share goes in.  true when any of them was already there (or occurs twice here).
+    bool insert_all(std::vector<uint64_t> &hs, std::vector<uint64_t> &scratch)
+    {
+        if (hs.empty()) return false;
+        uint32_t count[N_SHARDS + 1] = {0};
+        for (uint64_t &h : hs) { if (h == 0) h = EMPTY_ALIAS; ++count[(h >> (64 - SHARD_BITS)) + 1]; }
+        for (size_t k = 0; k < N_SHARDS; ++k) count[k + 1] += count[k];
+        scratch.resize(hs.size());
+        uint32_t at[N_SHARDS];
+        memcpy(at, count, sizeof at);
+        for (uint64_t h : hs) scratch[at[h >> (64 - SHARD_BITS)]++] = h;
+        bool dup = false;
+        for (size_t k = 0; k < N_SHARDS; ++k) {
+            if (count[k] == count[k + 1]) continue;
+            Shard &sh = shards_[k];
+            std::lock_guard<std::mutex> lk(sh.m);
+            for (uint32_t i = count[k]; i < count[k + 1]; ++i) dup |= insert_locked(sh, scratch[i]);
+        }
+        return dup;
+    }
+
+private:
+    static const int SHARD_BITS = 10;
+    static const size_t N_SHARDS = 1u << SHARD_BITS;
+    static const uint64_t EMPTY_ALIAS = 0x9E3779B97F4A7C15ull;   // 0 marks an empty slot
+    struct Shard { std::mutex m; std::vector<uint64_t> slots; size_t n = 0; };
+    static bool insert_locked(Shard &sh, uint64_t h)
+    {
         if (sh.slots.empty()) { sh.slots.assign(1u << 10, 0); }
         size_t mask = sh.slots.size() - 1, s = (h * 0xD6E8FEB86659FD93ull >> 20) & mask;
         while (sh.slots[s]) {
@@ -323,11 +354,6 @@ public:
         }
         return false;
     }
-
-private:
-    static const int SHARD_BITS = 10;
-    static const size_t N_SHARDS = 1u << SHARD_BITS;
-    struct Shard { std::mutex m; std::vector<uint64_t> slots; size_t n = 0; };
     std::vector<Shard> shards_;
 };
 
@@ -426,11 +452,11 @@ public:
             if (assume_grouped && out.error.empty()) {        // run heads inside the chunk; record 0 is the consumer's business
                 const size_t n = out.size();
                 out.new_run.assign(n, 0);
+                std::vector<uint64_t> hs, scratch;
+                hs.reserve(n);
                 for (size_t i = 1; i < n; ++i)
-                    if (!out.same_key(i, i - 1)) {
-                        out.new_run[i] = 1;
-                        if (heads.insert(out.hash[i])) came_back.store(true, std::memory_order_relaxed);
-                    }
+                    if (!out.same_key(i, i - 1)) { out.new_run[i] = 1; hs.push_back(out.hash[i]); }
+                if (heads.insert_all(hs, scratch)) came_back.store(true, std::memory_order_relaxed);
             }
         });
         std::string frame_err;
