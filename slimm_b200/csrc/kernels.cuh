@@ -47,6 +47,13 @@ struct RecSoA {
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(ref + i); }
     __device__ __forceinline__ u32 upos(u32 i) const { return (u32)__ldg(pos + i); }
+    // records i .. i+3 with three 128-bit loads (i a multiple of 4, arrays 16-byte aligned)
+    __device__ __forceinline__ void load4(u32 i, uint4 &r, uint4 &g, uint4 &p) const
+    {
+        r = __ldg(reinterpret_cast<const uint4 *>(rid + i));
+        g = __ldg(reinterpret_cast<const uint4 *>(ref + i));
+        p = __ldg(reinterpret_cast<const uint4 *>(pos + i));
+    }
     // lanes 0..2 pull the 128-byte lines that hold record i of the three arrays towards the SM
     __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
     {
@@ -59,6 +66,13 @@ struct RecPacked {
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(&rp[i].x); }
     __device__ __forceinline__ u32 upos(u32 i) const { return __ldg(&rp[i].y); }
+    __device__ __forceinline__ void load4(u32 i, uint4 &r, uint4 &g, uint4 &p) const
+    {
+        r = __ldg(reinterpret_cast<const uint4 *>(rid + i));
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp + i)), b = __ldg(reinterpret_cast<const uint4 *>(rp + i + 2));
+        g = make_uint4(a.x, a.z, b.x, b.z);
+        p = make_uint4(a.y, a.w, b.y, b.w);
+    }
     __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
     {
         const void *a = lane == 0 ? (const void *)(rid + i) : lane == 1 ? (const void *)(rp + i) : (const void *)(rp + i + 16);
@@ -202,7 +216,7 @@ __device__ __forceinline__ u32 find_head(const Rec &rec, u32 c0, u32 n, u32 lane
 #define MAX_BUCKETS 512      // padded bin ids fit 31 bits, slices are >= 2^22 bins
 
 struct CovParams {
-    const uint4 *meta; u32 G, half_avg; BinDiv wdiv;
+    const uint4 *meta; const uint2 *meta2 /* {len, bin offset lo}: half the footprint, for histograms of fewer than 2^31 bins */; u32 G, half_avg; BinDiv wdiv;
     unsigned long long *hist;       // MODE 0
     u32 *items, *bucket_cnt; u32 shift, n_buckets;   // MODE 1
     u32 *cw, *cw_idx; uint2 *chunk_cnt; u32 *lr;     // compact stream of the multi-mapped reads for k_assign
@@ -294,7 +308,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
     if (tid == 0) { s_h = 0; s_u = 0; s_b = 0; }
     __syncthreads();
     u32 heads = 0, uniq = 0, bad = 0;
-    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 n_chunks = n / CHUNK + (n % CHUNK != 0);
     const u32 wg = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 c = wg; c < n_chunks; c += nw) {
         const u32 c0 = c * CHUNK, c1 = min(c0 + CHUNK, n);
@@ -373,6 +387,8 @@ k_coverage(Rec rec, u32 n, CovParams P)
         if (s_b) atomicOr(&P.sc->flags, s_b);
     }
 }
+
+#include "coverage_tile.cuh"
 
 // Per-slice bookkeeping shared by k_coverage (count), k_bucket_scan, k_split (cursor) and k_accumulate.
 struct Sched {
@@ -1377,7 +1393,7 @@ k_assign(Rec rec, u32 n, AssignParams P)
     const u32 lane = threadIdx.x & 31;
     for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
     __syncthreads();
-    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 n_chunks = n / CHUNK + (n % CHUNK != 0);
     const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 c = wg; c < n_chunks; c += nw) {
         const uint2 cnt = __ldg(P.chunk_cnt + c);
@@ -1504,7 +1520,7 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict_
     const u32 lane = threadIdx.x & 31;
     for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
     __syncthreads();
-    const u32 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u32 n_chunks = n / CHUNK + (n % CHUNK != 0);
     const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 c = wg; c < n_chunks; c += nw) {
         const uint2 cnt = __ldg(P.chunk_cnt + c);

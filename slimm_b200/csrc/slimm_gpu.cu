@@ -35,7 +35,7 @@ struct slimm_gpu_ctx {
     std::vector<u64> h_off;                 // [G+1] padded bin offsets
     u64 Bp = 0, B = 0;
     // device
-    uint4 *d_meta = nullptr; u32 *d_lin = nullptr; u32 *d_top_idx = nullptr; u64 *d_off = nullptr;
+    uint4 *d_meta = nullptr; uint2 *d_meta2 = nullptr; u32 *d_lin = nullptr; u32 *d_top_idx = nullptr; u64 *d_off = nullptr;
     unsigned long long *d_hist = nullptr; u32 *d_cov2 = nullptr;
     u32 *d_stats = nullptr; float *d_cp = nullptr; u32 *d_scratch = nullptr;
     u32 *d_valid_bits = nullptr; unsigned char *d_valid_bytes = nullptr;
@@ -50,6 +50,7 @@ struct slimm_gpu_ctx {
     BinDiv wdiv{0, 0, 0};
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
     int cutoff_mode = -1;                   // -1 auto (cluster/DSMEM sort when it fits), 1 global-memory sort
+    int cov_variant = 1;                    // 1: warp-private tiles (k_coverage_tile), 0: sliding 32-record windows (k_coverage)
     bool used_bucket = false;
     bool finished = false;                  // k_finish_assign ran
     std::unique_ptr<slimm_host::ProfilePlan> plan;
@@ -190,6 +191,11 @@ static int layout_bins(slimm_gpu_ctx *ctx)
         CU(cudaMemcpy(ctx->d_fine_ref, fr.data(), (n_fine + 1) * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(ctx->d_meta, meta.data(), (size_t)G * sizeof(uint4), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint2> meta2(G);
+        for (u32 g = 0; g < G; ++g) meta2[g] = make_uint2(meta[g].x, meta[g].z);
+        CU(cudaMemcpy(ctx->d_meta2, meta2.data(), (size_t)G * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(ctx->d_off, ctx->h_off.data(), ((size_t)G + 1) * 8, cudaMemcpyHostToDevice));
     return SLIMM_GPU_OK;
 }
@@ -230,6 +236,7 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     while (ctx->npow2 < G) ctx->npow2 <<= 1;
     ctx->assign_words = (u64)(17 + ctx->n_top) * G;
     CU(cudaMalloc(&ctx->d_meta, (size_t)G * sizeof(uint4)));
+    CU(cudaMalloc(&ctx->d_meta2, (size_t)G * sizeof(uint2)));
     CU(cudaMalloc(&ctx->d_off, ((size_t)G + 1) * 8));
     CU(cudaMalloc(&ctx->d_lin, (size_t)G * 32));
     CU(cudaMalloc(&ctx->d_top_idx, (size_t)G * 4));
@@ -249,6 +256,7 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
     if (const char *e = getenv("SLIMM_GPU_FINE")) ctx->fine_packed = strcmp(e, "wide") != 0;
     if (const char *e = getenv("SLIMM_GPU_ASSIGN")) ctx->assign_variant = !strcmp(e, "window") ? 0 : 1;
+    if (const char *e = getenv("SLIMM_GPU_COV")) ctx->cov_variant = !strcmp(e, "window") ? 0 : 1;
     if (G < 65536) {
         // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
         std::vector<unsigned short> l16((size_t)G * 8);
@@ -288,7 +296,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     free_records(ctx);
-    cudaFree(ctx->d_meta); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
+    cudaFree(ctx->d_meta); cudaFree(ctx->d_meta2); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
@@ -441,6 +449,24 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     return SLIMM_GPU_OK;
 }
 
+static bool aligned16(const RecSoA &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.ref) | ((uintptr_t)r.pos)) & 15u) == 0; }
+static bool aligned16(const RecPacked &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.rp)) & 15u) == 0; }
+
+// K1: the tile kernel (128-bit loads: the arrays must be 16-byte aligned), else the sliding windows
+template <class Rec, int MODE>
+static void launch_k_coverage(slimm_gpu_ctx *ctx, const Rec &rec, u32 n, const CovParams &P, bool extra, int grid)
+{
+    if (ctx->cov_variant == 1 && aligned16(rec)) {
+        const u64 n_chunks = ((u64)n + CHUNK - 1) / CHUNK;
+        const int warps = COVT_THREADS / 32;
+        const int tgrid = (int)std::max<u64>(1, std::min<u64>((n_chunks + warps - 1) / warps, (u64)ctx->sm_count * 4));
+        const size_t dyn = (size_t)warps * COVT_WARP_WORDS * 4;
+        if (extra) k_coverage_tile<Rec, MODE, true><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
+        else k_coverage_tile<Rec, MODE, false><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
+    } else if (extra) k_coverage<Rec, MODE, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+    else k_coverage<Rec, MODE, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+}
+
 template <class Rec>
 static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
@@ -468,13 +494,12 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     }
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
     CovParams P{};
-    P.meta = ctx->d_meta; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
+    P.meta = ctx->d_meta; P.meta2 = ctx->d_meta2; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
     P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr; P.rs = ctx->d_rs;
     P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.sc = ctx->d_sc;
     if (!ctx->used_bucket) {
         TimeScope ts(ctx, SLIMM_GPU_T_COVERAGE);
-        if (want_idx || P.res_kind) k_coverage<Rec, 0, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-        else k_coverage<Rec, 0, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        launch_k_coverage<Rec, 0>(ctx, rec, n, P, want_idx || P.res_kind, grid);
         ctx->launches++;
         CU(cudaGetLastError());
         return SLIMM_GPU_OK;
@@ -492,8 +517,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         CU(cudaMemsetAsync(ctx->d_sched, 0, sizeof(Sched), ctx->stream));
         P.items = ctx->d_items; P.shift = shift; P.n_buckets = n_buckets;
         P.bucket_cnt = reinterpret_cast<u32 *>(reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count));
-        if (want_idx || P.res_kind) k_coverage<Rec, 1, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-        else k_coverage<Rec, 1, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
+        launch_k_coverage<Rec, 1>(ctx, rec, n, P, want_idx || P.res_kind, grid);
         ctx->launches++;
     }
     {
