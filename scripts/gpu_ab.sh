@@ -1,12 +1,14 @@
 #!/bin/bash
-# A/B of kernel variants selected by environment variables: parity tests, then the default bench per variant.
+# A/B of kernel variants selected by environment variables: parity tests (unless SKIP_TESTS=1), then the default bench per variant.
 # usage: gpu_ab.sh "VAR=a VAR2=b" "VAR=c" ...   (each argument is one variant's environment; "" = defaults)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+if [ -z "$SKIP_TESTS" ]; then
+  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+fi
 i=0
 for V in "$@"; do
   i=$((i+1))
-  env $V timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
+  env $V timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e $BENCH_ARGS > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
   echo "variant $i [$V] rc=$?"; tail -2 gpurun_out/ab_$i.err
   python -c "
 import json

@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libslimm_gpu.so")
-    log = os.path.join(HERE, "csrc", "ptxas.log")
+    log = os.path.join(HERE, "ptxas.log")   # git-ignored: registers / spills / shared memory per kernel of the last build
     with open(log, "w") as f:
         f.write(r.stdout + r.stderr)
     if verbose:

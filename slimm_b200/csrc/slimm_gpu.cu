@@ -471,7 +471,7 @@ template <class Rec>
 static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
 {
     const u32 n = (u32)ctx->n;
-    const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
+    const u64 n_chunks = ((u64)n + CHUNK - 1) / CHUNK;
     static const int cov_ctas = getenv("SLIMM_COV_CTAS") ? atoi(getenv("SLIMM_COV_CTAS")) : 6;   // CTAs per SM (experiments)
     const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * cov_ctas));
     // compact stream of the multi-mapped reads (k_assign's input), one slot per chunk
@@ -926,7 +926,7 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     u32 *uniq2 = ctx->d_assign, *lca = uniq2 + G, *cm = lca + (u64)8 * G, *fb = cm + (u64)8 * G;
     if (ctx->n) {
         const u32 n = (u32)ctx->n;
-        const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
+        const u64 n_chunks = ((u64)n + CHUNK - 1) / CHUNK;
         const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 8));
         AssignParams P{};
         P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
