@@ -196,6 +196,9 @@ __device__ __forceinline__ void covt_phase_a(const Rec &rec, const CovParams &P,
                                              u32 s_cnt_addr, u32 &bad)
 {
     Quad cur = load_quad(rec, t0 + 4 * lane, rem > 4 * lane ? rem - 4 * lane : 0u, WHOLE || rem >= 128u);
+    // read id of the first record behind a step (lane 31's last record needs it): fetched by lane 0 one step ahead of its use,
+    // so that nothing waits on the quad that was only just requested
+    u32 ra = (lane == 0 && (WHOLE || rem > 128u)) ? rec.read(t0 + 128u) : 0u;
 #pragma unroll 2
     for (u32 s = 0; s < COVT_STEPS; ++s) {
         const u32 o = s * 128u;
@@ -206,18 +209,20 @@ __device__ __forceinline__ void covt_phase_a(const Rec &rec, const CovParams &P,
         const u32 left = WHOLE ? COVT_T - o : rem - o;             // records from this step on (at least: enough to tell a whole step)
         const bool has_after = WHOLE ? (s + 1 < COVT_STEPS || rem > COVT_T) : left > 128u;
         Quad nx = cur;
-        u32 r_after = r_halo;
+        u32 ra_next = 0;
         if (s + 1 < COVT_STEPS && has_after) {                     // the next step's loads fly during this step's work
             const u32 l2 = left - 128u;
             nx = load_quad(rec, t0 + o + 128u + 4 * lane, l2 > 4 * lane ? l2 - 4 * lane : 0u, WHOLE || l2 >= 128u);
-            r_after = __shfl_sync(FULL, nx.r.x, 0);
+            if (s + 2 < COVT_STEPS && lane == 0 && (WHOLE || l2 > 128u)) ra_next = rec.read(t0 + o + 256u);
         }
+        const u32 r_after = s + 1 < COVT_STEPS ? __shfl_sync(FULL, ra, 0) : r_halo;
         const u32 mine = left > 4 * lane ? left - 4 * lane : 0u;
         if (WHOLE || left >= 128u)
             covt_step<Rec, MODE, EXTRA, true>(P, cur, t0 + o + 4 * lane, mine, lane, carry, t0 + o == 0, r_after, has_after, sg + 32 + o, hb + 1 + 4 * s, s_cnt_addr, bad);
         else
             covt_step<Rec, MODE, EXTRA, false>(P, cur, t0 + o + 4 * lane, mine, lane, carry, t0 + o == 0, r_after, has_after, sg + 32 + o, hb + 1 + 4 * s, s_cnt_addr, bad);
         cur = nx;
+        ra = ra_next;
     }
 }
 
@@ -245,7 +250,7 @@ k_coverage_tile(const __grid_constant__ Rec rec, u32 n, const __grid_constant__ 
         u32 n_cw = 0, n_lr = 0, n_rs = 0;                          // compact words / long reads / multi-target reads of this chunk (warp-uniform)
         u32 *const cw_c = P.cw + (u64)c * CW_SLOT;
         u32 *const cwi_c = EXTRA && P.cw_idx ? P.cw_idx + (u64)c * CW_SLOT : nullptr;
-        unsigned short *const rs_c = P.rs + (u64)c * RS_SLOT;
+        u32 *const rs_c = P.rs + (u64)c * RS_SLOT;
         const u32 c0 = c * CHUNK;
         for (u32 tt = 0; tt < CHUNK && n - c0 > tt; tt += COVT_T) {
             const u32 t0 = c0 + tt, rem = n - t0;                  // rem >= 1 records from t0 on
@@ -313,40 +318,41 @@ k_coverage_tile(const __grid_constant__ Rec rec, u32 n, const __grid_constant__ 
                 const u32 LB = __ballot_sync(FULL, act && lng);    // more than 32 records: the whole warp, below
                 if (LB) { if (act && lng) llist[n_long + __popc(LB & LANE_LT(lane))] = (unsigned short)p; n_long += __popc(LB); }
                 const bool go = act && !lng;
-                u32 rep = 0;                                       // bit i: record i of the read repeats an earlier reference of the read
-                bool multi = false;
-                if (go) {
-                    const u32 g0 = sg[p];
-                    u64 seen = 1ull << covt_hash6(g0);
-                    for (u32 i = 1; i < len; ++i) {
-                        const u32 g = sg[p + i];
-                        const u64 bit = 1ull << covt_hash6(g);
-                        if (seen & bit) {                          // maybe seen before: look
-                            bool r = false;
-                            for (u32 t = 0; t < i; ++t) r |= sg[p + t] == g;
-                            rep |= (u32)r << i;
-                        }
-                        seen |= bit;
-                        multi |= g != g0;
-                    }
-                }
                 const bool owned = go && p >= 32;                  // the read starts inside this tile: count it, emit its words
-                const u32 cdist = (owned && multi) ? len - __popc(rep) : 0u;   // distinct references -> compact words
-                u32 incl = cdist;
+                // room for the compact words is reserved BEFORE the walk, one word per record (an upper bound: repeat hits
+                // leave gaps; every entry of rs carries its own word count), so the walk can write them as it goes
+                u32 incl = owned ? len : 0u;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += y; }
-                const u32 EB = __ballot_sync(FULL, cdist != 0);
-                if (cdist) {
-                    u32 o = n_cw + incl - cdist;
-                    rs_c[n_rs + __popc(EB & LANE_LT(lane))] = (unsigned short)o;
-                    for (u32 i = 0; i < len; ++i)
-                        if (!((rep >> i) & 1u)) {
-                            cw_c[o] = sg[p + i] | (i == 0 ? CW_HEAD : 0u);
-                            if (EXTRA && cwi_c) cwi_c[o] = t0 + p + i - 32u;
-                            ++o;
-                        }
-                }
+                const u32 o_start = n_cw + incl - (owned ? len : 0u);
                 n_cw += __shfl_sync(FULL, incl, 31);
+                u32 rep = 0;                                       // bit i: record i of the read repeats an earlier reference of the read
+                bool multi = false;
+                u32 o = o_start;
+                if (go) {
+                    const u32 g0 = sg[p];
+                    // references within +-32 of the first one have a bit of their own in `near` (exact); the others are hashed into
+                    // `far` and confirmed by a look at the earlier records
+                    u64 near = 1ull << 32, far = 0;
+                    if (owned) { cw_c[o] = g0 | CW_HEAD; if (EXTRA && cwi_c) cwi_c[o] = t0 + p - 32u; ++o; }
+                    for (u32 i = 1; i < len; ++i) {
+                        const u32 g = sg[p + i];
+                        const u32 d = g - g0 + 32u;
+                        bool r;
+                        if (d < 64u) { r = (near >> d) & 1ull; near |= 1ull << d; }
+                        else {
+                            const u64 bit = 1ull << covt_hash6(g);
+                            r = false;
+                            if (far & bit) for (u32 t = 1; t < i; ++t) r |= sg[p + t] == g;
+                            far |= bit;
+                        }
+                        rep |= (u32)r << i;
+                        multi |= g != g0;
+                        if (owned && !r) { cw_c[o] = g; if (EXTRA && cwi_c) cwi_c[o] = t0 + p + i - 32u; ++o; }
+                    }
+                }
+                const u32 EB = __ballot_sync(FULL, owned && multi);
+                if (owned && multi) rs_c[n_rs + __popc(EB & LANE_LT(lane))] = o_start | ((o - o_start) << 16);
                 n_rs += __popc(EB);
                 if (go) {
                     const u32 jb = t0 + p - 32u;                   // record index of the read's first record

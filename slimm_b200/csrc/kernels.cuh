@@ -220,7 +220,7 @@ struct CovParams {
     unsigned long long *hist;       // MODE 0
     u32 *items, *bucket_cnt; u32 shift, n_buckets;   // MODE 1
     u32 *cw, *cw_idx; uint2 *chunk_cnt; u32 *lr;     // compact stream of the multi-mapped reads for k_assign
-    unsigned short *rs;                              // per chunk: where every multi-target read starts inside the chunk's compact words
+    u32 *rs;                                         // per chunk, one entry per multi-target read: start inside the chunk's compact words | words << 16
     unsigned char *res_kind;        // optional per-read results: marks the head of every single-target read
     DevScalars *sc;
 };
@@ -316,7 +316,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
         u32 n_cw = 0, n_lr = 0, n_rs = 0;                          // compact words / long runs / multi-target reads of this chunk (warp-uniform)
         u32 *const cw_c = P.cw + (u64)c * CW_SLOT;
         u32 *const cwi_c = EXTRA && P.cw_idx ? P.cw_idx + (u64)c * CW_SLOT : nullptr;
-        unsigned short *const rs_c = P.rs + (u64)c * RS_SLOT;
+        u32 *const rs_c = P.rs + (u64)c * RS_SLOT;
         WinRegs cur = fetch_window(rec, p, n, lane);
         while (p < c1) {
             Window win;
@@ -352,7 +352,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
                     const u32 local = n_cw + __popc(C & LANE_LT(lane));
                     cw_c[local] = g | (is_head ? CW_HEAD : 0u);
                     if (EXTRA && cwi_c) cwi_c[local] = p + lane;
-                    if (is_head) rs_c[n_rs + __popc(Hm & LANE_LT(lane))] = (unsigned short)local;
+                    if (is_head) rs_c[n_rs + __popc(Hm & LANE_LT(lane))] = local | ((u32)__popc(C & win.M) << 16);
                 }
                 n_cw += __popc(C);
                 n_rs += __popc(Hm);
@@ -1385,88 +1385,6 @@ __device__ __noinline__ void assign_long_run(const Rec &rec, u32 p, u32 n, u32 l
     }
 }
 
-template <class Rec>
-__global__ void __launch_bounds__(256)
-k_assign(Rec rec, u32 n, AssignParams P)
-{
-    __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
-    const u32 lane = threadIdx.x & 31;
-    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
-    __syncthreads();
-    const u32 n_chunks = n / CHUNK + (n % CHUNK != 0);
-    const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (u32 c = wg; c < n_chunks; c += nw) {
-        const uint2 cnt = __ldg(P.chunk_cnt + c);
-        const u32 m = cnt.x;                                       // compact words of this chunk
-        const u32 *cw = P.cw + (u64)c * CW_SLOT;
-        u32 p = 0;
-        while (p < m) {
-            const u32 i = p + lane;
-            const bool in = i < m;
-            if (lane == 0 && p + PREFETCH_AHEAD < m) asm volatile("prefetch.global.L1 [%0];" ::"l"(cw + p + PREFETCH_AHEAD));
-            const u32 word = in ? __ldcs(cw + i) : 0u;
-            u32 nxw = __shfl_down_sync(FULL, word, 1);
-            if (lane == 31 && i + 1 < m) nxw = __ldcs(cw + i + 1);
-            const bool last = in && (i + 1 >= m || (nxw & CW_HEAD));
-            const u32 H = __ballot_sync(FULL, in && (word & CW_HEAD)), E = __ballot_sync(FULL, last);
-            Window win;
-            window_masks(H, E, min(32u, m - p), p, m, lane, in, win);   // every run is at most 32 words: none is long
-            const u32 g = word & ~CW_HEAD;
-            const bool v = win.whole && is_valid(P.vb, g);
-            const u32 V = __ballot_sync(FULL, v);
-            const u32 Vm = V & win.M;                              // surviving references of my read
-            const int f = Vm ? __ffs(Vm) - 1 : (int)lane;
-            const u32 g0 = __shfl_sync(FULL, g, f);                // first survivor in file order
-            const bool d = v && g != g0;
-            const u32 Dm = __ballot_sync(FULL, d);
-            const bool run_multi = (Dm & win.M) != 0;              // |S| >= 2
-            const bool is_head = win.whole && (int)lane == win.s;
-            if (is_head && Vm && !run_multi) {                     // sole survivor: the read became unique through the filter
-                atomicAdd(P.uniq2_extra + g0, 1u);
-                if (P.cw_idx) {
-                    const u32 lead = P.cw_idx[(u64)c * CW_SLOT + p + f];
-                    if (P.cov2) atomicAdd(P.cov2 + bin_of(P.meta, g0, rec.upos(lead), P.half_avg, P.wdiv), 1u);
-                    if (P.res_kind) { const u32 hd = P.cw_idx[(u64)c * CW_SLOT + i]; P.res_kind[hd] = 1; P.res_val[hd] = g0; }
-                }
-            }
-            if (Dm) {                                              // some read of this window needs an LCA
-                u32 mine = 0;
-                if (d) {
-                    const uint4 a0 = __ldg(P.lin4 + 2 * (u64)g0), b0 = __ldg(P.lin4 + 2 * (u64)g0 + 1);
-                    mine = lineage_diff(P.lin4, g, a0, b0);
-                }
-                // OR of the difference masks over the lanes of my read: segmented suffix scan by shuffles, as many
-                // steps as the longest read of the window needs (REDUX with one mask per read serialises over the masks)
-                const int span = (int)__reduce_max_sync(FULL, run_multi ? (u32)(win.e - win.s) : 0u);
-                u32 acc = mine, gm = v ? g : 0u;
-                for (int dd = 1; dd <= span; dd <<= 1) {
-                    const u32 t = __shfl_down_sync(FULL, acc, dd), tg = __shfl_down_sync(FULL, gm, dd);
-                    if (win.whole && (int)lane + dd <= win.e) { acc |= t; gm = max(gm, tg); }
-                }
-                const int hd_lane = win.whole ? win.s : (int)lane;
-                const u32 eq = ~__shfl_sync(FULL, acc, hd_lane) & 0xFFu;
-                const bool fb = run_multi && eq == 0;
-                const u32 top = __shfl_sync(FULL, gm, hd_lane);           // largest surviving reference id of the read
-                const u32 owner = fb ? top : g0;
-                const u32 level = fb ? 7u : (u32)(__ffs(eq) - 1);
-                if (v && run_multi) mark_child(P, g, fb, level, owner);
-                const bool is_lca = is_head && run_multi;
-                if (is_lca && P.res_kind) {
-                    const u32 hd = P.cw_idx[(u64)c * CW_SLOT + i];
-                    P.res_kind[hd] = 2;
-                    P.res_val[hd] = __ldg(reinterpret_cast<const u32 *>(P.lin4) + (u64)owner * 8 + level);
-                }
-                if (is_lca) count_lca(s_key, s_val, P.lca_cnt, owner * 8 + level);
-            }
-            p = win.next > p ? win.next : p + 32;
-        }
-        for (u32 k = 0; k < (cnt.y & 0xFFu); ++k) assign_long_run(rec, __ldg(P.lr + c * LR_SLOT + k), n, lane, P, s_key, s_val);
-    }
-    __syncthreads();
-    for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x)
-        if (s_key[k] != LCA_EMPTY && s_val[k]) atomicAdd(P.lca_cnt + s_key[k], s_val[k]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // K5+K6, one THREAD per multi-target read.  k_coverage lists, per chunk, where every multi-target read
 // starts inside the chunk's compact words (rs); a warp takes a chunk and its lanes take 32 reads at a time.
@@ -1514,7 +1432,7 @@ __device__ __forceinline__ u32 lin_neq(const Lin32 &acc)
 // EXTRA: uniq_cov2 bins / per-read results are wanted (they need the record index of every compact word)
 template <class Rec, class Lin, bool EXTRA>
 __global__ void __launch_bounds__(256, EXTRA ? 4 : ASSIGN_READS_OCC)
-k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
+k_assign_reads(Rec rec, u32 n, AssignParams P, const u32 *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
 {
     __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
     const u32 lane = threadIdx.x & 31;
@@ -1524,15 +1442,14 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const unsigned short *__restrict_
     const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 c = wg; c < n_chunks; c += nw) {
         const uint2 cnt = __ldg(P.chunk_cnt + c);
-        const u32 m = cnt.x, n_lr = cnt.y & 0xFFu, n_rs = cnt.y >> 8;   // compact words, long runs, multi-target reads of the chunk
+        const u32 n_lr = cnt.y & 0xFFu, n_rs = cnt.y >> 8;               // long runs, multi-target reads of the chunk
         const u32 *cw = P.cw + (u64)c * CW_SLOT;
-        const unsigned short *rs = rs_all + (u64)c * RS_SLOT;
+        const u32 *rs = rs_all + (u64)c * RS_SLOT;
         for (u32 k0 = 0; k0 < n_rs; k0 += 32) {
             const u32 k = k0 + lane;
-            const u32 start = k < n_rs ? (u32)__ldg(rs + k) : m;
-            u32 end = __shfl_down_sync(FULL, start, 1);
-            if (lane == 31) end = k + 1 < n_rs ? (u32)__ldg(rs + k + 1) : m;
             if (k >= n_rs) continue;
+            const u32 entry = __ldg(rs + k);                       // start | words << 16 (at most 32 words)
+            const u32 start = entry & 0xFFFFu, end = start + (entry >> 16);
             u32 g0 = 0, j0 = start, ns = 0, gmax = 0, vmask = 0;  // vmask: which of the read's (at most 32) words survive
             Lin l0, acc;
             lin_zero(l0); lin_zero(acc);

@@ -44,9 +44,8 @@ struct slimm_gpu_ctx {
     u32 *d_items = nullptr, *d_grouped = nullptr; u64 items_cap = 0; u32 bucket_shift = 22;
     Sched *d_sched = nullptr;
     u32 *d_cw = nullptr, *d_cw_idx = nullptr, *d_lr = nullptr; uint2 *d_chunk_cnt = nullptr; u64 cw_chunks = 0;   // compact stream for k_assign
-    unsigned short *d_rs = nullptr;         // starts of the multi-target reads inside every chunk's compact words
+    u32 *d_rs = nullptr;                    // per chunk: start | words << 16 of every multi-target read inside the chunk's compact words
     uint4 *d_lin16 = nullptr;               // lineages as 8 x 16-bit per-level dense taxon indices (fewer than 65536 references)
-    int assign_variant = 1;                 // 1: one thread per multi-target read, 0: sliding windows over the compact words
     BinDiv wdiv{0, 0, 0};
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
     int cutoff_mode = -1;                   // -1 auto (cluster/DSMEM sort when it fits), 1 global-memory sort
@@ -255,7 +254,6 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
     CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
     if (const char *e = getenv("SLIMM_GPU_FINE")) ctx->fine_packed = strcmp(e, "wide") != 0;
-    if (const char *e = getenv("SLIMM_GPU_ASSIGN")) ctx->assign_variant = !strcmp(e, "window") ? 0 : 1;
     if (const char *e = getenv("SLIMM_GPU_COV")) ctx->cov_variant = !strcmp(e, "window") ? 0 : 1;
     if (G < 65536) {
         // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
@@ -479,7 +477,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     if (ctx->cw_chunks < n_chunks) {
         cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt); cudaFree(ctx->d_rs);
         ctx->d_cw = ctx->d_cw_idx = ctx->d_lr = nullptr; ctx->d_chunk_cnt = nullptr; ctx->d_rs = nullptr; ctx->cw_chunks = 0;
-        CU(cudaMalloc(&ctx->d_rs, n_chunks * RS_SLOT * 2));
+        CU(cudaMalloc(&ctx->d_rs, n_chunks * RS_SLOT * 4));
         CU(cudaMalloc(&ctx->d_cw, n_chunks * CW_SLOT * 4));
         if (want_idx) CU(cudaMalloc(&ctx->d_cw_idx, n_chunks * CW_SLOT * 4));
         CU(cudaMalloc(&ctx->d_lr, n_chunks * LR_SLOT * 4));
@@ -927,7 +925,6 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
     if (ctx->n) {
         const u32 n = (u32)ctx->n;
         const u64 n_chunks = ((u64)n + CHUNK - 1) / CHUNK;
-        const int grid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * 8));
         AssignParams P{};
         P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr;
         P.meta = ctx->d_meta; P.lin4 = (const uint4 *)ctx->d_lin; P.top_idx = ctx->d_top_idx; P.vb = ctx->d_valid_bits;
@@ -940,16 +937,14 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
         const bool extra = ctx->d_cw_idx != nullptr || P.res_kind != nullptr;
         if (ctx->use_sorted) {
             const RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
-            if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-            else if (extra && ctx->d_lin16) k_assign_reads<RecPacked, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            if (extra && ctx->d_lin16) k_assign_reads<RecPacked, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
             else if (extra) k_assign_reads<RecPacked, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             else if (ctx->d_lin16) k_assign_reads<RecPacked, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
             else k_assign_reads<RecPacked, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, (const u32 *)ctx->d_rp_sorted, 2, ctx->d_valid_bits, n);
         } else {
             const RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
-            if (!ctx->assign_variant) k_assign<<<grid, 256, 0, ctx->stream>>>(rec, n, P);
-            else if (extra && ctx->d_lin16) k_assign_reads<RecSoA, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            if (extra && ctx->d_lin16) k_assign_reads<RecSoA, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
             else if (extra) k_assign_reads<RecSoA, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
             else if (ctx->d_lin16) k_assign_reads<RecSoA, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
             else k_assign_reads<RecSoA, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
