@@ -47,13 +47,13 @@ struct RecSoA {
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(ref + i); }
     __device__ __forceinline__ u32 upos(u32 i) const { return (u32)__ldg(pos + i); }
-    // records i .. i+3 with three 128-bit loads (i a multiple of 4, arrays 16-byte aligned)
-    __device__ __forceinline__ void load4(u32 i, uint4 &r, uint4 &g, uint4 &p) const
+    // records i .. i+3 with 128-bit loads (i a multiple of 4, arrays 16-byte aligned)
+    __device__ __forceinline__ void load_rg4(u32 i, uint4 &r, uint4 &g) const
     {
         r = __ldg(reinterpret_cast<const uint4 *>(rid + i));
         g = __ldg(reinterpret_cast<const uint4 *>(ref + i));
-        p = __ldg(reinterpret_cast<const uint4 *>(pos + i));
     }
+    __device__ __forceinline__ uint4 load_p4(u32 i) const { return __ldg(reinterpret_cast<const uint4 *>(pos + i)); }
     // lanes 0..2 pull the 128-byte lines that hold record i of the three arrays towards the SM
     __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
     {
@@ -66,12 +66,16 @@ struct RecPacked {
     __device__ __forceinline__ u32 read(u32 i) const { return __ldg(rid + i); }
     __device__ __forceinline__ u32 refid(u32 i) const { return __ldg(&rp[i].x); }
     __device__ __forceinline__ u32 upos(u32 i) const { return __ldg(&rp[i].y); }
-    __device__ __forceinline__ void load4(u32 i, uint4 &r, uint4 &g, uint4 &p) const
+    __device__ __forceinline__ void load_rg4(u32 i, uint4 &r, uint4 &g) const
     {
         r = __ldg(reinterpret_cast<const uint4 *>(rid + i));
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp + i)), b = __ldg(reinterpret_cast<const uint4 *>(rp + i + 2));
         g = make_uint4(a.x, a.z, b.x, b.z);
-        p = make_uint4(a.y, a.w, b.y, b.w);
+    }
+    __device__ __forceinline__ uint4 load_p4(u32 i) const
+    {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp + i)), b = __ldg(reinterpret_cast<const uint4 *>(rp + i + 2));
+        return make_uint4(a.y, a.w, b.y, b.w);
     }
     __device__ __forceinline__ void prefetch(u32 i, u32 lane) const
     {
@@ -223,6 +227,7 @@ struct CovParams {
     u32 *rs;                                         // per chunk, one entry per multi-target read: start inside the chunk's compact words | words << 16
     unsigned char *res_kind;        // optional per-read results: marks the head of every single-target read
     DevScalars *sc;
+    cudaTextureObject_t meta2_tex;                   // meta2 behind the texture path (k_coverage_tile, TEXG)
 };
 
 // contribution of one record: direct RED into the interleaved histogram, or a 32-bit item

@@ -35,6 +35,7 @@ struct slimm_gpu_ctx {
     std::vector<u64> h_off;                 // [G+1] padded bin offsets
     u64 Bp = 0, B = 0;
     // device
+    cudaTextureObject_t meta2_tex = 0; int cov_gather = 0;   // 1: meta2 through the texture path in k_coverage_tile (default; SLIMM_COV_GATHER=ldg: plain loads)
     uint4 *d_meta = nullptr; uint2 *d_meta2 = nullptr; u32 *d_lin = nullptr; u32 *d_top_idx = nullptr; u64 *d_off = nullptr;
     unsigned long long *d_hist = nullptr; u32 *d_cov2 = nullptr;
     u32 *d_stats = nullptr; float *d_cp = nullptr; u32 *d_scratch = nullptr;
@@ -236,6 +237,16 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     ctx->assign_words = (u64)(17 + ctx->n_top) * G;
     CU(cudaMalloc(&ctx->d_meta, (size_t)G * sizeof(uint4)));
     CU(cudaMalloc(&ctx->d_meta2, (size_t)G * sizeof(uint2)));
+    {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = ctx->d_meta2; rd.res.linear.desc = cudaCreateChannelDesc<uint2>(); rd.res.linear.sizeInBytes = (size_t)G * sizeof(uint2);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        if (G <= (1u << 27)) CU(cudaCreateTextureObject(&ctx->meta2_tex, &rd, &td, nullptr));
+    }
+    ctx->cov_gather = ctx->meta2_tex ? 1 : 0;
+    if (const char *e = getenv("SLIMM_COV_GATHER")) ctx->cov_gather = strcmp(e, "ldg") && ctx->meta2_tex ? 1 : 0;
     CU(cudaMalloc(&ctx->d_off, ((size_t)G + 1) * 8));
     CU(cudaMalloc(&ctx->d_lin, (size_t)G * 32));
     CU(cudaMalloc(&ctx->d_top_idx, (size_t)G * 4));
@@ -294,6 +305,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     free_records(ctx);
+    if (ctx->meta2_tex) cudaDestroyTextureObject(ctx->meta2_tex);
     cudaFree(ctx->d_meta); cudaFree(ctx->d_meta2); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
@@ -459,8 +471,9 @@ static void launch_k_coverage(slimm_gpu_ctx *ctx, const Rec &rec, u32 n, const C
         const int warps = COVT_THREADS / 32;
         const int tgrid = (int)std::max<u64>(1, std::min<u64>((n_chunks + warps - 1) / warps, (u64)ctx->sm_count * 4));
         const size_t dyn = (size_t)warps * COVT_WARP_WORDS * 4;
-        if (extra) k_coverage_tile<Rec, MODE, true><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
-        else k_coverage_tile<Rec, MODE, false><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
+        if (extra) k_coverage_tile<Rec, MODE, true, false><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
+        else if (ctx->cov_gather == 1 && MODE == 1) k_coverage_tile<Rec, MODE, false, true><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
+        else k_coverage_tile<Rec, MODE, false, false><<<tgrid, COVT_THREADS, dyn, ctx->stream>>>(rec, n, P);
     } else if (extra) k_coverage<Rec, MODE, true><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
     else k_coverage<Rec, MODE, false><<<grid, 256, 0, ctx->stream>>>(rec, n, P);
 }
@@ -492,7 +505,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
     }
     if (ctx->d_kind) CU(cudaMemsetAsync(ctx->d_kind, 0, std::max<u64>(ctx->n, 1), ctx->stream));
     CovParams P{};
-    P.meta = ctx->d_meta; P.meta2 = ctx->d_meta2; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
+    P.meta = ctx->d_meta; P.meta2 = ctx->d_meta2; P.meta2_tex = ctx->meta2_tex; P.G = ctx->G; P.half_avg = ctx->avg / 2u; P.wdiv = ctx->wdiv; P.hist = ctx->d_hist;
     P.cw = ctx->d_cw; P.cw_idx = ctx->d_cw_idx; P.chunk_cnt = ctx->d_chunk_cnt; P.lr = ctx->d_lr; P.rs = ctx->d_rs;
     P.res_kind = (ctx->flags & SLIMM_GPU_READ_RESULTS) ? ctx->d_kind : nullptr; P.sc = ctx->d_sc;
     if (!ctx->used_bucket) {
