@@ -122,8 +122,12 @@ def make_contigs(n_genomes: int, rng: np.random.Generator, accessions: List[str]
 
 def make_records(contigs: Contigs, n_records: int, rng: np.random.Generator,
                  multi_frac: float = 0.2, k_lo: int = 2, k_hi: int = 8, neigh: int = 8,
-                 repeat_frac: float = 0.002, read_len: int = 100, shuffle: bool = False) -> Records:
-    """Records of a read are contiguous and read ids ascend in file order unless ``shuffle``."""
+                 repeat_frac: float = 0.002, read_len: int = 100, shuffle: bool = False,
+                 neigh_mode: str = "index") -> Records:
+    """Records of a read are contiguous and read ids ascend in file order unless ``shuffle``.
+    ``neigh_mode`` "taxonomy": a multi-mapped read draws a level (species 40 %, genus 30 %, family 15 %, order 8 %,
+    class 4 %, phylum 3 %) and its extra targets uniformly among the genomes sharing that taxon with the primary one
+    (fan-out of ``make_taxonomy``), so that LCAs land on every rank."""
     G = len(contigs.lengths)
     mean_k = (1.0 - multi_frac) + multi_frac * 0.5 * (k_lo + k_hi)
     n_reads = max(1, int(np.ceil(n_records / (mean_k * (1.0 + repeat_frac)))) + 16)
@@ -141,8 +145,15 @@ def make_records(contigs: Contigs, n_records: int, rng: np.random.Generator,
     read_of = np.repeat(np.arange(n_reads, dtype=np.int64), k)
     start = np.cumsum(k) - k
     j = np.arange(read_of.size, dtype=np.int64) - start[read_of]
-    off = rng.integers(1, neigh + 1, size=read_of.size) * rng.choice((-1, 1), size=read_of.size)
-    ref = np.where(j == 0, primary[read_of], np.clip(primary[read_of] + off, 0, G - 1))
+    if neigh_mode == "taxonomy":
+        sizes = np.array([4, 16, 64, 128, 256, 512], dtype=np.int64)
+        lvl = np.minimum(np.searchsorted(np.array([0.40, 0.70, 0.85, 0.93, 0.97, 1.0]), rng.random(n_reads)), 5)
+        size = sizes[lvl][read_of]
+        pick = np.minimum((rng.random(read_of.size) * size).astype(np.int64), size - 1)
+        ref = np.where(j == 0, primary[read_of], np.clip((primary[read_of] // size) * size + pick, 0, G - 1))
+    else:
+        off = rng.integers(1, neigh + 1, size=read_of.size) * rng.choice((-1, 1), size=read_of.size)
+        ref = np.where(j == 0, primary[read_of], np.clip(primary[read_of] + off, 0, G - 1))
     # planted repeat hits: the repeated record directly follows the original
     times = 1 + rep.astype(np.int64)
     read_of = np.repeat(read_of, times)

@@ -24,7 +24,13 @@ class DeviceRecords:
 
 def make_records_device(lengths: np.ndarray, weights: np.ndarray, n_records: int, device, seed: int = 12345,
                         multi_frac: float = 0.2, k_lo: int = 2, k_hi: int = 8, neigh: int = 8,
-                        repeat_frac: float = 0.002, read_len: int = 100, shuffle: bool = False) -> DeviceRecords:
+                        repeat_frac: float = 0.002, read_len: int = 100, shuffle: bool = False,
+                        neigh_mode: str = "index", read_id_base: int = 0) -> DeviceRecords:
+    """``neigh_mode``: "index" - extra targets of a multi-mapped read come from the +-``neigh`` index neighbourhood;
+    "taxonomy" - every multi-mapped read draws a level (species 40 %, genus 30 %, family 15 %, order 8 %, class 4 %,
+    phylum 3 %) and its extra targets uniformly among the genomes that share that taxon with the primary one
+    (fan-out 4/4/4/2/2/2 of ``synth.make_taxonomy``), so LCAs land on every rank.
+    ``read_id_base`` is added to every read id (block-wise generation: a block's ids stay disjoint from the others')."""
     G = int(lengths.size)
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -49,11 +55,22 @@ def make_records_device(lengths: np.ndarray, weights: np.ndarray, n_records: int
     read_of = torch.repeat_interleave(torch.arange(R, dtype=torch.int32, device=device), k64, output_size=total)
     j0 = torch.arange(total, dtype=torch.int64, device=device) == start[read_of.long()]
     del start, k64, k
-    off = torch.randint(1, neigh + 1, (total,), generator=gen, device=device, dtype=torch.int32)
-    sign = torch.randint(0, 2, (total,), generator=gen, device=device, dtype=torch.int32) * 2 - 1
     p = primary[read_of.long()]
-    ref = torch.where(j0, p, (p + off * sign).clamp_(0, G - 1))
-    del off, sign, p, j0, primary
+    if neigh_mode == "taxonomy":
+        sizes = torch.tensor([4, 16, 64, 128, 256, 512], dtype=torch.int32, device=device)      # genomes under a species .. phylum
+        cum = torch.tensor([0.40, 0.70, 0.85, 0.93, 0.97, 1.0], dtype=torch.float32, device=device)
+        lvl = torch.searchsorted(cum, torch.rand(R, generator=gen, device=device)).clamp_(max=5)
+        size = sizes[lvl][read_of.long()]
+        pick = (torch.rand(total, generator=gen, device=device) * size.to(torch.float32)).to(torch.int32).clamp_(max=511)
+        pick = torch.minimum(pick, size - 1)
+        ref = torch.where(j0, p, ((p // size) * size + pick).clamp_(0, G - 1))
+        del sizes, cum, lvl, size, pick
+    else:
+        off = torch.randint(1, neigh + 1, (total,), generator=gen, device=device, dtype=torch.int32)
+        sign = torch.randint(0, 2, (total,), generator=gen, device=device, dtype=torch.int32) * 2 - 1
+        ref = torch.where(j0, p, (p + off * sign).clamp_(0, G - 1))
+        del off, sign
+    del p, j0, primary
     # planted repeat hits directly after the original record
     times = (torch.rand(total, generator=gen, device=device) < repeat_frac).to(torch.int64) + 1
     total2 = int(times.sum().item())
@@ -72,6 +89,8 @@ def make_records_device(lengths: np.ndarray, weights: np.ndarray, n_records: int
         pos[a:b] = (u * span[ref[a:b].long()]).to(torch.int32)
         del u
     n_reads = int(read_of[-1].item()) + 1
+    if read_id_base:
+        read_of += read_id_base
     if shuffle:
         perm = torch.randperm(n_records, generator=gen, device=device)
         read_of, ref, pos = read_of[perm].contiguous(), ref[perm].contiguous(), pos[perm].contiguous()
