@@ -427,34 +427,38 @@ __global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_bu
 // MATCH.ANY over ~400 distinct slices is 8x slower), orders the tile by slice in shared memory and copies
 // every slice's share to its reserved place in the output, so the global stores are runs of consecutive words.
 // ------------------------------------------------------------------------------------------------
-#define SPLIT_ITEMS 32
-#define SPLIT_TILE (256 * SPLIT_ITEMS)
+#define SPLIT_TILE 8192
 // PEER: every slice has its own destination (dest[slice]: where THIS rank's items of the slice go inside the receive
 // buffer of the rank that owns the slice - local memory or a peer's, mapped over NVLink): the all-to-all of a sharded
 // run happens inside the split, tile by tile, as plain stores.
-template <bool PEER>
-__global__ void __launch_bounds__(256)
+// NT threads x (SPLIT_TILE / NT) items: the same tile with fewer registers per thread buys resident warps (256 x 32: 92 registers,
+// 16 warps per SM; 512 x 16: 32 warps per SM).
+template <bool PEER, int NT>
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2)
 k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, u32 *const *__restrict__ dest)
 {
+    constexpr int ITEMS = SPLIT_TILE / NT, NW = NT / 32;
+    constexpr int SCAN_T = NT < MAX_BUCKETS ? NT : MAX_BUCKETS;    // threads that take part in the scan of the slice counts
+    constexpr int HALVES = MAX_BUCKETS / SCAN_T;
     __shared__ u32 s_cnt[MAX_BUCKETS];         // items of each slice in this tile, then the slice's tile-local start
     __shared__ u32 s_delta[MAX_BUCKETS];       // global start - tile-local start (mod 2^32)
     __shared__ u32 *s_dst[PEER ? MAX_BUCKETS : 1];   // PEER: destination of the slice's first item of this tile, minus the tile-local start
     __shared__ u32 s_item[SPLIT_TILE];
-    __shared__ u32 s_warp_tot[8];
+    __shared__ u32 s_warp_tot[NW];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (u32 b = tid; b < MAX_BUCKETS; b += 256) s_cnt[b] = 0;
+        for (u32 b = tid; b < MAX_BUCKETS; b += NT) s_cnt[b] = 0;
         __syncthreads();
         const u64 t0 = tile * SPLIT_TILE;
-        u32 item[SPLIT_ITEMS], where[SPLIT_ITEMS];             // where: slice << 16 | rank inside (tile, slice)
+        u32 item[ITEMS], where[ITEMS];                         // where: slice << 16 | rank inside (tile, slice)
 #pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k) {
-            const u64 i = t0 + (u64)k * 256 + tid;
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * NT + tid;
             item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
         }
 #pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k) {
+        for (int k = 0; k < ITEMS; ++k) {
             where[k] = 0xFFFFFFFFu;
             if (item[k] != ITEM_SKIP) {
                 const u32 bk = (item[k] & 0x7FFFFFFFu) >> shift;
@@ -462,12 +466,12 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
             }
         }
         __syncthreads();
-        // exclusive scan of the slice counts over the tile (two slices per thread, halves in order)
-        u32 tot[2], excl[2], base = 0;
+        // exclusive scan of the slice counts over the tile (HALVES slices per scanning thread, halves in order)
+        u32 tot[HALVES], excl[HALVES], base = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const u32 b = tid + h * 256;
-            tot[h] = b < n_buckets ? s_cnt[b] : 0u;
+        for (int h = 0; h < HALVES; ++h) {
+            const u32 b = tid + h * SCAN_T;
+            tot[h] = (tid < SCAN_T && b < n_buckets) ? s_cnt[b] : 0u;
             u32 x = tot[h];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
@@ -475,15 +479,15 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
             __syncthreads();
             u32 wbase = 0, all = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
+            for (int k = 0; k < SCAN_T / 32; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
             excl[h] = base + wbase + x - tot[h];
             base += all;
             __syncthreads();
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const u32 b = tid + h * 256;
-            if (b < n_buckets) {
+        for (int h = 0; h < HALVES; ++h) {
+            const u32 b = tid + h * SCAN_T;
+            if (tid < SCAN_T && b < n_buckets) {
                 s_cnt[b] = excl[h];
                 if (tot[h]) {
                     const u32 at = atomicAdd(&sd->cursor[b], tot[h]);
@@ -494,7 +498,7 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < SPLIT_ITEMS; ++k)
+        for (int k = 0; k < ITEMS; ++k)
             if (where[k] != 0xFFFFFFFFu) {
                 const u32 bk = where[k] >> 16;
                 const u32 pos = s_cnt[bk] + (where[k] & 0xFFFFu);
@@ -502,7 +506,7 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
             }
         __syncthreads();
         const u32 total = base;                                // items of this tile (thread-uniform)
-        for (u32 j = tid; j < total; j += 256) {               // the slice of an item is a function of the item
+        for (u32 j = tid; j < total; j += NT) {                // the slice of an item is a function of the item
             const u32 v = s_item[j], bk = (v & 0x7FFFFFFFu) >> shift;
             if (PEER) s_dst[bk][j] = v; else out[j + s_delta[bk]] = v;
         }

@@ -459,6 +459,20 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     return SLIMM_GPU_OK;
 }
 
+// K1b: shape of the split CTAs (SLIMM_SPLIT_NT = 256 | 512 | 1024 threads over the same 8192-item tile)
+template <bool PEER>
+static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 n, u32 shift, u32 n_buckets, u32 *out, u32 *const *dest)
+{
+    static const int nt = getenv("SLIMM_SPLIT_NT") ? atoi(getenv("SLIMM_SPLIT_NT")) : 512;
+    const int per_sm = nt >= 1024 ? 1 : 2;
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+    const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * per_sm));
+    (void)sgrid;
+    if (nt == 256) k_split<PEER, 256><<<grid, 256, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
+    else if (nt >= 1024) k_split<PEER, 1024><<<grid, 1024, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
+    else k_split<PEER, 512><<<grid, 512, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
+}
+
 static bool aligned16(const RecSoA &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.ref) | ((uintptr_t)r.pos)) & 15u) == 0; }
 static bool aligned16(const RecPacked &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.rp)) & 15u) == 0; }
 
@@ -538,7 +552,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
         if (ctx->shard_n > 1 && ctx->p2p) { ctx->split_pending = true; ctx->launches += 1; }   // slimm_gpu_split_to_peers splits straight into the owners' buffers
         else {
-            k_split<false><<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, shift, n_buckets, ctx->d_sched, ctx->d_grouped, nullptr);
+            launch_k_split<false>(ctx, sgrid, ctx->d_items, n, shift, n_buckets, ctx->d_grouped, nullptr);
             ctx->launches += 2;
         }
     }
@@ -861,7 +875,7 @@ int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts, uin
         const u32 n = (u32)ctx->n;
         const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
-        k_split<true><<<sgrid, 256, 0, ctx->stream>>>(ctx->d_items, n, ctx->bucket_shift, ns, ctx->d_sched, nullptr, ctx->d_dest);
+        launch_k_split<true>(ctx, sgrid, ctx->d_items, n, ctx->bucket_shift, ns, nullptr, ctx->d_dest);
         ctx->launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(ctx->stream));   // dest is a host vector; and the caller's barrier comes next anyway
