@@ -39,6 +39,8 @@ struct DevScalars {
     float cut, ucut;
     u32 done_ctr;
     u32 pad;
+    float tot[2];                 // K4: in-order f32 sum of cov_percent / uniq_cov_percent over the references with unique reads
+    u32 n_members[2];             // K4: how many references that is (the same number twice)
 };
 
 // record accessors: plain SoA, or {read_id[], packed (ref | pos<<32)[]} after the device sort
@@ -1139,153 +1141,202 @@ __device__ __forceinline__ u32 *dsm_key(cgx::cluster_group &cl, u32 *keys, u32 i
     return cl.map_shared_rank(keys, idx >> share_log) + (idx & ((1u << share_log) - 1u));
 }
 
+// K4 in three kernels, so that the two order-sensitive f32 chains (each one dependent addition per reference: ~100 us at
+// 50 000 references, whatever the hardware) run CONCURRENTLY instead of back to back behind the sort:
+//   k_cut_fold          (side stream)  total = std::accumulate(v, 0.0f) in ascending reference order
+//   k_cut_sort_cluster  (main stream)  members -> distributed shared memory, bitonic sort, sorted keys to global memory, and the
+//                                      descending running sums P_k = v[n-1] + v[n-2] + ... (k terms) - the `sub` of
+//                                      get_quantile_cut_off after k trips, which does not depend on the total
+//   k_cut_finish        (after both)   first k with !(P_k / total < q) by a PARALLEL search (same comparison, same operands,
+//                                      monotone in k), cut-off = v[n-1-k]; then the valid set and the -v counters
+#define FOLD_CHUNK 4096
+__global__ void __launch_bounds__(1024)
+k_cut_fold(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, DevScalars *sc)
+{
+    __shared__ float s_buf[2][FOLD_CHUNK];
+    const u32 which = blockIdx.x, tid = threadIdx.x;
+    float total = 0.0f;                                            // thread 0's copy is the fold
+    // references without unique reads add +0.0f: exact, and the chain stays free of branches
+    auto stage = [&](u32 c0, float *buf, u32 first, u32 step) {
+        for (u32 k = first; k < FOLD_CHUNK; k += step) {
+            const u32 g = c0 + k;
+            float x = 0.0f;
+            if (g < G && stats[4 * g + 3] > 0) x = __fdiv_rn((float)stats[4 * g + 2 * which], (float)__ldg(&meta[g].y));
+            buf[k] = x;
+        }
+    };
+    stage(0, s_buf[0], tid, 1024);
+    __syncthreads();
+    u32 cur = 0;
+    for (u32 c0 = 0; c0 < G; c0 += FOLD_CHUNK) {                   // the other warps stage the next chunk while thread 0 folds this one
+        if (tid >= 32 && c0 + FOLD_CHUNK < G) stage(c0 + FOLD_CHUNK, s_buf[cur ^ 1], tid - 32, 992);
+        if (tid == 0) total = fold_in_order(total, s_buf[cur], min((u32)FOLD_CHUNK, G - c0));
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (tid == 0) sc->tot[which] = total;
+}
+
 __global__ void __cluster_dims__(CUT_CL, 1, 1) __launch_bounds__(1024)
-k_cutoffs_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float q, u32 min_reads,
-                  float *__restrict__ cp_all /*[2][G]*/, u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes,
-                  DevScalars *sc)
+k_cut_sort_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float *__restrict__ cp_all /*[2][G]*/,
+                   u32 *__restrict__ sorted /*[2][G] ascending*/, float *__restrict__ prefix /*[2][G]: P_0 = 0, P_k*/, DevScalars *sc)
 {
     extern __shared__ u32 s_keys[];           // this CTA's share of the distributed key array
     cgx::cluster_group cl = cgx::this_cluster();
     const u32 rank = cl.block_rank();
     const u32 which = blockIdx.x / CUT_CL;    // 0: cov, 1: uniq_cov
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float *cp = cp_all + (size_t)which * G;
+    __shared__ u32 s_part[CUT_CL];            // members per range of references (one range per CTA)
+    __shared__ u32 s_warp[32];
+    __shared__ float s_p[CUT_CHUNK];
+    __shared__ float s_carry;
+    // the references are cut into CUT_CL ranges; every CTA counts the members of all of them (cheap, and nobody has to wait)
+    const u32 per = (G + CUT_CL - 1) / CUT_CL;
+    if (tid < CUT_CL) s_part[tid] = 0;
+    __syncthreads();
+    for (u32 r = 0; r < CUT_CL; ++r) {
+        u32 c = 0;
+        for (u32 g = r * per + tid; g < min(G, (r + 1) * per); g += 1024) c += stats[4 * g + 3] > 0;
+        c = warp_sum(c);
+        if (lane == 0 && c) atomicAdd(&s_part[r], c);
+    }
+    __syncthreads();
+    u32 n = 0, my_base = 0;
+    for (u32 r = 0; r < CUT_CL; ++r) { if (r < rank) my_base += s_part[r]; n += s_part[r]; }
+    u32 m = CUT_CL * 1024;                    // padded size: a power of two, at least one key per thread
+    while (m < n) m <<= 1;
+    const u32 share_log = 31 - __clz(m / CUT_CL), share = 1u << share_log;
+    for (u32 k = tid; k < share; k += 1024) s_keys[k] = 0xFFFFFFFFu;
+    cl.sync();                                // every share initialised
+    // my range: cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155) for everybody, the members' keys
+    // into the distributed array, in reference order
+    {
+        u32 run = my_base;
+        for (u32 g0 = rank * per; g0 < min(G, (rank + 1) * per); g0 += 1024) {
+            const u32 g = g0 + tid;
+            const bool in = g < min(G, (rank + 1) * per);
+            float x = 0.0f;
+            bool keep = false;
+            if (in) {
+                x = __fdiv_rn((float)stats[4 * g + 2 * which], (float)meta[g].y);
+                cp[g] = x;
+                keep = stats[4 * g + 3] > 0;
+            }
+            const u32 bal = __ballot_sync(FULL, keep);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            __syncthreads();
+            u32 wbase = 0, tot = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { const u32 t = s_warp[k]; if (k < (int)wid) wbase += t; tot += t; }
+            if (keep) *dsm_key(cl, s_keys, run + wbase + __popc(bal & LANE_LT(lane)), share_log) = __float_as_uint(x);
+            run += tot;
+            __syncthreads();
+        }
+    }
+    cl.sync();
+    // bitonic sort, ascending (values are >= 0: u32 order == f32 order)
+    for (u32 k = 2; k <= m; k <<= 1)
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            if (j >= share) {                 // partner lives in another CTA: the lower rank of the pair works
+                const u32 prank = rank ^ (j >> share_log);
+                if (prank > rank) {
+                    u32 *other = cl.map_shared_rank(s_keys, prank);
+                    for (u32 o = tid; o < share; o += 1024) {
+                        const u32 t = (rank << share_log) | o;
+                        const u32 a = s_keys[o], b = other[o];
+                        const bool up = (t & k) == 0;
+                        if ((a > b) == up) { s_keys[o] = b; other[o] = a; }
+                    }
+                }
+                cl.sync();
+            } else {
+                for (u32 o = tid; o < share; o += 1024) {
+                    const u32 po = o ^ j;
+                    if (po > o) {
+                        const u32 t = (rank << share_log) | o;
+                        const u32 a = s_keys[o], b = s_keys[po];
+                        const bool up = (t & k) == 0;
+                        if ((a > b) == up) { s_keys[o] = b; s_keys[po] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    cl.sync();
+    // my share of the sorted keys -> global memory
+    for (u32 o = tid; o < share; o += 1024) {
+        const u32 t = (rank << share_log) | o;
+        if (t < n) sorted[(size_t)which * G + t] = s_keys[o];
+    }
+    if (rank == 0) {
+        // P_0 = 0, P_k = P_{k-1} + v[n-k]: one thread, the values staged CUT_CHUNK at a time by the whole CTA
+        if (tid == 0) { s_carry = 0.0f; sc->n_members[which] = n; }
+        float *P = prefix + (size_t)which * G;
+        for (u32 k0 = 0; k0 < n; k0 += CUT_CHUNK) {                // P_{k0} .. P_{k0 + cn - 1}
+            const u32 cn = min((u32)CUT_CHUNK, n - k0);
+            // s_p[k] = v[n - (k0 + k)] for k >= 1 (the term that makes P_{k0+k} out of P_{k0+k-1}); s_p[0] pairs with the carry
+            for (u32 k = tid; k < cn; k += 1024) {
+                const u32 kk = k0 + k;
+                s_p[k] = kk == 0 ? 0.0f : __uint_as_float(*dsm_key(cl, s_keys, n - kk, share_log));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float run = s_carry;
+                u32 k = 0;
+                for (; k + 16 <= cn; k += 16) {
+                    float x[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) x[t] = s_p[k + t];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) { run = __fadd_rn(run, x[t]); s_p[k + t] = run; }
+                }
+                for (; k < cn; ++k) { run = __fadd_rn(run, s_p[k]); s_p[k] = run; }
+                s_carry = run;
+            }
+            __syncthreads();
+            for (u32 k = tid; k < cn; k += 1024) P[k0 + k] = s_p[k];
+            __syncthreads();
+        }
+    }
+    cl.sync();                                // nobody leaves while rank 0 may still read its share
+}
+
+// one CTA: both cut-offs by a parallel search over the running sums, then the valid set
+__global__ void __launch_bounds__(1024)
+k_cut_finish(const u32 *__restrict__ stats, u32 G, float q, u32 min_reads, const float *__restrict__ cp_all, const u32 *__restrict__ sorted,
+             const float *__restrict__ prefix, u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes, DevScalars *sc)
+{
+    __shared__ u32 s_k[2];
+    const u32 tid = threadIdx.x;
     if (min_reads == 0) {                     // -mr default: 1 + (matches_count-1)/10000 (src/slimm.hpp:458-459)
         const u32 R = (u32)sc->n_reads;
         min_reads = R ? 1u + (R - 1u) / 10000u : 0u;
     }
-    const u32 tid = threadIdx.x;
-    float *cp = cp_all + (size_t)which * G;
-    __shared__ u32 s_scan[1024];
-    __shared__ float s_buf[CUT_CHUNK];
-    __shared__ u32 s_base, s_i, s_n;
-    __shared__ float s_f;
-    __shared__ int s_done;
-    __shared__ bool s_last;
-
-    // cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155); the cluster shares the work
-    for (u32 g = rank * 1024 + tid; g < G; g += CUT_CL * 1024)
-        cp[g] = __fdiv_rn((float)stats[4 * g + 2 * which], (float)meta[g].y);
-    // members: references with unique reads.  Every CTA counts them (the padded size must be known everywhere)
-    u32 cnt = 0;
-    for (u32 g = tid; g < G; g += 1024) cnt += stats[4 * g + 3] > 0;
-    cnt = warp_sum(cnt);
-    if (tid == 0) s_n = 0;
+    const u32 n = sc->n_members[0];
+    if (tid < 2) s_k[tid] = n ? n - 1 : 0;    // the loop also ends when i reaches 0, i.e. after n - 1 trips
     __syncthreads();
-    if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
+    if (q < 1.0f && n > 0) {
+        for (u32 which = 0; which < 2; ++which) {
+            const float total = sc->tot[which];
+            const float *P = prefix + (size_t)which * G;
+            // i = n-1; while ((sub/total) < q && i > 0) { sub += v[i]; --i; }: after k trips sub == P_k
+            u32 best = 0xFFFFFFFFu;
+            for (u32 k = tid; k < n; k += 1024)
+                if (!(__fdiv_rn(P[k], total) < q)) { best = k; break; }   // my smallest k that stops the loop (k ascends)
+            if (best != 0xFFFFFFFFu) atomicMin(&s_k[which], best);
+        }
+    }
     __syncthreads();
-    const u32 n = s_n;
-    float cut = 0.0f;
-    const bool active = q < 1.0f && n > 0;    // cluster-uniform
-    u32 m = CUT_CL * 1024;                    // padded size: a power of two, at least one key per thread
-    while (m < n) m <<= 1;
-    const u32 share_log = 31 - __clz(m / CUT_CL), share = 1u << share_log;
-    if (active) {
-        for (u32 k = tid; k < share; k += 1024) s_keys[k] = 0xFFFFFFFFu;
-        if (tid == 0) { s_base = 0; s_f = 0.0f; }
-    }
-    cl.sync();                                // cp[] complete (global) and every share initialised
-    if (active && rank == 0) {
-        // total = std::accumulate(v, 0.0f) in ascending reference order; the same pass scatters the keys
-        for (u32 g0 = 0; g0 < G; g0 += 1024) {
-            const u32 g = g0 + tid;
-            const u32 keep = (g < G && stats[4 * g + 3] > 0) ? 1u : 0u;
-            const float x = keep ? __ldcg(cp + g) : 0.0f;
-            // rank among the members of this batch of 1024 references: ballot inside the warp, warp totals through shared memory
-            const u32 bal = __ballot_sync(FULL, keep != 0);
-            if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
-            __syncthreads();
-            u32 wbase = 0, tot = 0;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) { const u32 t = s_scan[k]; if (k < (int)(tid >> 5)) wbase += t; tot += t; }
-            const u32 base = s_base, pos = wbase + __popc(bal & LANE_LT(tid & 31));
-            if (keep) {
-                s_buf[pos] = x;
-                *dsm_key(cl, s_keys, base + pos, share_log) = __float_as_uint(x);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                s_f = fold_in_order(s_f, s_buf, tot);
-                s_base = base + tot;
-            }
-            __syncthreads();
-        }
-    }
-    if (active) {
-        cl.sync();
-        // bitonic sort, ascending (values are >= 0: u32 order == f32 order)
-        for (u32 k = 2; k <= m; k <<= 1)
-            for (u32 j = k >> 1; j > 0; j >>= 1) {
-                if (j >= share) {             // partner lives in another CTA: the lower rank of the pair works
-                    const u32 prank = rank ^ (j >> share_log);
-                    if (prank > rank) {
-                        u32 *other = cl.map_shared_rank(s_keys, prank);
-                        for (u32 o = tid; o < share; o += 1024) {
-                            const u32 t = (rank << share_log) | o;
-                            const u32 a = s_keys[o], b = other[o];
-                            const bool up = (t & k) == 0;
-                            if ((a > b) == up) { s_keys[o] = b; other[o] = a; }
-                        }
-                    }
-                    cl.sync();
-                } else {
-                    for (u32 o = tid; o < share; o += 1024) {
-                        const u32 po = o ^ j;
-                        if (po > o) {
-                            const u32 t = (rank << share_log) | o;
-                            const u32 a = s_keys[o], b = s_keys[po];
-                            const bool up = (t & k) == 0;
-                            if ((a > b) == up) { s_keys[o] = b; s_keys[po] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-        cl.sync();
-    }
-    if (active && rank == 0) {
-        const float total = s_f;
-        // i = n-1; while ((sub/total) < q && i > 0) { sub += v[i]; --i; }  cutoff = v[i]
-        if (tid == 0) {
-            s_done = (!(total > 0.0f) || !(q > 0.0f));   // 0/0 = NaN: NaN < q is false; q <= 0: never true
-            s_i = n - 1;
-            float s = 0.0f;
-            if (!s_done) {
-                // (sub/total) < q  <=>  sub < s*, s* = smallest f32 with fl(s*/total) >= q
-                // (x -> fl(x/total) is monotone), so the loop needs no division
-                s = __fmul_rn(q, total);
-                if (s <= 0.0f) s = __uint_as_float(1u);
-                while (__fdiv_rn(s, total) >= q && s > __uint_as_float(1u)) s = f32_down(s);
-                while (__fdiv_rn(s, total) < q) s = f32_up(s);
-            }
-            s_f = s;
-        }
-        __syncthreads();
-        const float sstar = s_f;
-        float sub = 0.0f;                                           // only thread 0's copy matters
-        u32 c_hi = n;                                               // values [c_lo, c_hi) staged, walked downwards
-        while (!s_done) {
-            const u32 c_lo = c_hi > CUT_CHUNK ? c_hi - CUT_CHUNK : 0;
-            for (u32 k = tid; k < c_hi - c_lo; k += 1024) s_buf[k] = __uint_as_float(*dsm_key(cl, s_keys, c_lo + k, share_log));
-            __syncthreads();
-            if (tid == 0) {
-                u32 i = s_i;
-                walk_chunk(s_buf, c_lo, i, sub, sstar);
-                s_i = i;
-                if (!(sub < sstar) || i == 0 || c_lo == 0) s_done = 1;
-            }
-            __syncthreads();
-            c_hi = c_lo;
-        }
-        cut = __uint_as_float(*dsm_key(cl, s_keys, s_i, share_log));
-    }
-    cl.sync();                                // nobody leaves while rank 0 may still read its share
-    if (rank != 0) return;
     if (tid == 0) {
-        if (which == 0) sc->cut = cut; else sc->ucut = cut;
-        __threadfence();
-        s_last = atomicAdd(&sc->done_ctr, 1u) == 1u;
+        float c0 = 0.0f, c1 = 0.0f;
+        if (q < 1.0f && n > 0) {
+            c0 = __uint_as_float(sorted[n - 1 - s_k[0]]);
+            c1 = __uint_as_float(sorted[(size_t)G + n - 1 - s_k[1]]);
+        }
+        sc->cut = c0; sc->ucut = c1;
     }
     __syncthreads();
-    if (!s_last) return;
     cutoffs_valid_set(stats, G, min_reads, cp_all, valid_bits, valid_bytes, sc);
 }
 

@@ -26,7 +26,8 @@ enum { ST_CREATED = 0, ST_COVERAGE = 1, ST_FILTER = 2, ST_ASSIGN = 3 };
 struct slimm_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
-    cudaEvent_t zero_start = nullptr, zero_done = nullptr;
+    cudaEvent_t zero_start = nullptr, zero_done = nullptr, stats_ready = nullptr, fold_done = nullptr;
+    u32 *d_cut_sorted = nullptr; float *d_cut_prefix = nullptr;   // K4: sorted cov_percent keys and their descending running sums, [2][G] each
     bool own_stream = true;
     cudaEvent_t upload_done = nullptr;
     u32 G = 0, w = 0, avg = 0, flags = 0, n_top = 0, npow2 = 1;
@@ -217,6 +218,8 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->zero_start, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->zero_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->stats_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->fold_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) { CU(cudaEventCreate(&ctx->ev[i][0])); CU(cudaEventCreate(&ctx->ev[i][1])); }
     const u32 G = ctx->G = cfg->n_refs;
@@ -259,7 +262,9 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_sched, sizeof(Sched)));
     if (const char *e = getenv("SLIMM_GPU_TAIL")) ctx->tail_mode = !strcmp(e, "host") ? 1 : -1;
     if (const char *e = getenv("SLIMM_GPU_CUTOFF")) ctx->cutoff_mode = !strcmp(e, "global") ? 1 : -1;
-    CU(cudaFuncSetAttribute(k_cutoffs_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
+    CU(cudaFuncSetAttribute(k_cut_sort_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CUT_SHARE * 4));
+    CU(cudaMalloc(&ctx->d_cut_sorted, (size_t)cfg->n_refs * 8));
+    CU(cudaMalloc(&ctx->d_cut_prefix, (size_t)cfg->n_refs * 8));
     if (const char *e = getenv("SLIMM_GPU_ACC")) ctx->acc_mode = !strcmp(e, "l2") ? 0 : 1;
     if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "SLIMM_GPU_SKIP_BINS and SLIMM_GPU_KEEP_UNIQ_COV2 exclude each other");
     CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
@@ -322,6 +327,9 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->zero_start) cudaEventDestroy(ctx->zero_start);
     if (ctx->zero_done) cudaEventDestroy(ctx->zero_done);
+    if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
+    if (ctx->fold_done) cudaEventDestroy(ctx->fold_done);
+    cudaFree(ctx->d_cut_sorted); cudaFree(ctx->d_cut_prefix);
     delete ctx;
     return SLIMM_GPU_OK;
 }
@@ -917,12 +925,20 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
     }
     {
         TimeScope ts(ctx, SLIMM_GPU_T_CUTOFF);
-        if (ctx->G <= (u32)CUT_CL * CUT_SHARE && ctx->cutoff_mode != 1) {   // sort in the distributed shared memory of a cluster
+        if (ctx->G <= (u32)CUT_CL * CUT_SHARE && ctx->cutoff_mode != 1) {
+            // the in-order total on the side stream, under the cluster sort + running sums; then the parallel search (kernels.cuh, K4)
+            CU(cudaEventRecord(ctx->stats_ready, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->stats_ready, 0));
+            k_cut_fold<<<2, 1024, 0, ctx->aux_stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, ctx->d_sc);
+            CU(cudaEventRecord(ctx->fold_done, ctx->aux_stream));
             u32 m = CUT_CL * 1024;
             while (m < ctx->G) m <<= 1;
             const size_t dyn = (size_t)(m / CUT_CL) * 4;
-            k_cutoffs_cluster<<<2 * CUT_CL, 1024, dyn, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp,
-                                                                      ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
+            k_cut_sort_cluster<<<2 * CUT_CL, 1024, dyn, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix, ctx->d_sc);
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->fold_done, 0));
+            k_cut_finish<<<1, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix,
+                                                      ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
+            ctx->launches += 2;
         } else {
             k_cutoffs<<<2, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_scratch,
                                                    ctx->npow2, ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
