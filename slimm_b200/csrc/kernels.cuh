@@ -41,6 +41,8 @@ struct DevScalars {
     u32 pad;
     float tot[2];                 // K4: in-order f32 sum of cov_percent / uniq_cov_percent over the references with unique reads
     u32 n_members[2];             // K4: how many references that is (the same number twice)
+    u32 tot_ready[2];             // K4: tot[] is final (k_cut_fold runs beside k_cut_sort_cluster, which peeks)
+    u32 k_done[2];                // K4: running sums P_0 .. P_{k_done-1} exist (the chain ends early once the stop is certain)
 };
 
 // record accessors: plain SoA, or {read_id[], packed (ref | pos<<32)[]} after the device sort
@@ -958,16 +960,51 @@ __device__ __forceinline__ void walk_chunk(const float *buf, u32 c_lo, u32 &i, f
 // that the only serial chain is the additions themselves
 __device__ __forceinline__ float fold_in_order(float total, const float *buf, u32 n)
 {
+    // the next sixteen values are loaded while the current sixteen are added: the additions (4 cycles each, one after the other)
+    // are the only thing the thread ever waits for
+    float x[16], y[16];
     u32 k = 0;
-    for (; k + 16 <= n; k += 16) {
-        float x[16];
+    if (n >= 16) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) x[t] = buf[k + t];
+        for (int t = 0; t < 16; ++t) x[t] = buf[t];
+        for (; k + 32 <= n; k += 16) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) y[t] = buf[k + 16 + t];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) total = __fadd_rn(total, x[t]);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) x[t] = y[t];
+        }
 #pragma unroll
         for (int t = 0; t < 16; ++t) total = __fadd_rn(total, x[t]);
+        k += 16;
     }
     for (; k < n; ++k) total = __fadd_rn(total, buf[k]);
     return total;
+}
+
+// running sums in place: buf[k] = carry + buf[0] + ... + buf[k] (one rounding per addition, in order); returns the last one
+__device__ __forceinline__ float running_sums_in_order(float run, float *buf, u32 n)
+{
+    float x[16], y[16];
+    u32 k = 0;
+    if (n >= 16) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) x[t] = buf[t];
+        for (; k + 32 <= n; k += 16) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) y[t] = buf[k + 16 + t];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) { run = __fadd_rn(run, x[t]); buf[k + t] = run; }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) x[t] = y[t];
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { run = __fadd_rn(run, x[t]); buf[k + t] = run; }
+        k += 16;
+    }
+    for (; k < n; ++k) { run = __fadd_rn(run, buf[k]); buf[k] = run; }
+    return run;
 }
 
 // valid set + -v counters (src/slimm.hpp:354-378); one CTA of 1024 threads, after both cut-offs are known
@@ -1150,6 +1187,7 @@ __device__ __forceinline__ u32 *dsm_key(cgx::cluster_group &cl, u32 *keys, u32 i
 //   k_cut_finish        (after both)   first k with !(P_k / total < q) by a PARALLEL search (same comparison, same operands,
 //                                      monotone in k), cut-off = v[n-1-k]; then the valid set and the -v counters
 #define FOLD_CHUNK 4096
+#define PREFIX_CHUNK 2048
 __global__ void __launch_bounds__(1024)
 k_cut_fold(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, DevScalars *sc)
 {
@@ -1174,66 +1212,54 @@ k_cut_fold(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G,
         __syncthreads();
         cur ^= 1;
     }
-    if (tid == 0) sc->tot[which] = total;
+    if (tid == 0) { sc->tot[which] = total; __threadfence(); *(volatile u32 *)&sc->tot_ready[which] = 1u; }
 }
 
 __global__ void __cluster_dims__(CUT_CL, 1, 1) __launch_bounds__(1024)
-k_cut_sort_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float *__restrict__ cp_all /*[2][G]*/,
+k_cut_sort_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta, u32 G, float q, float *__restrict__ cp_all /*[2][G]*/,
                    u32 *__restrict__ sorted /*[2][G] ascending*/, float *__restrict__ prefix /*[2][G]: P_0 = 0, P_k*/, DevScalars *sc)
 {
     extern __shared__ u32 s_keys[];           // this CTA's share of the distributed key array
     cgx::cluster_group cl = cgx::this_cluster();
     const u32 rank = cl.block_rank();
     const u32 which = blockIdx.x / CUT_CL;    // 0: cov, 1: uniq_cov
-    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 tid = threadIdx.x, lane = tid & 31;
     float *cp = cp_all + (size_t)which * G;
-    __shared__ u32 s_part[CUT_CL];            // members per range of references (one range per CTA)
-    __shared__ u32 s_warp[32];
-    __shared__ float s_p[CUT_CHUNK];
+    __shared__ u32 s_n;                       // rank 0's copy counts the members of the whole cluster
+    __shared__ float s_p[PREFIX_CHUNK];
     __shared__ float s_carry;
-    // the references are cut into CUT_CL ranges; every CTA counts the members of all of them (cheap, and nobody has to wait)
-    const u32 per = (G + CUT_CL - 1) / CUT_CL;
-    if (tid < CUT_CL) s_part[tid] = 0;
-    __syncthreads();
-    for (u32 r = 0; r < CUT_CL; ++r) {
-        u32 c = 0;
-        for (u32 g = r * per + tid; g < min(G, (r + 1) * per); g += 1024) c += stats[4 * g + 3] > 0;
-        c = warp_sum(c);
-        if (lane == 0 && c) atomicAdd(&s_part[r], c);
-    }
-    __syncthreads();
-    u32 n = 0, my_base = 0;
-    for (u32 r = 0; r < CUT_CL; ++r) { if (r < rank) my_base += s_part[r]; n += s_part[r]; }
-    u32 m = CUT_CL * 1024;                    // padded size: a power of two, at least one key per thread
-    while (m < n) m <<= 1;
+    __shared__ int s_stop;
+    // padded size: a power of two that holds every reference (how many have unique reads is only known after the pass below)
+    u32 m = CUT_CL * 1024;
+    while (m < G) m <<= 1;
     const u32 share_log = 31 - __clz(m / CUT_CL), share = 1u << share_log;
     for (u32 k = tid; k < share; k += 1024) s_keys[k] = 0xFFFFFFFFu;
-    cl.sync();                                // every share initialised
-    // my range: cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155) for everybody, the members' keys
-    // into the distributed array, in reference order
+    if (tid == 0) s_n = 0;
+    cl.sync();                                // every share initialised, the counter zeroed
+    // my range of references: cov_percent = float(nz) / number_of_bins (src/reference_contig.hpp:148-155) for everybody; the members'
+    // keys go to the distributed array, a warp's batch at the place a cluster-wide counter hands out (their order does not matter:
+    // they are sorted next)
     {
-        u32 run = my_base;
-        for (u32 g0 = rank * per; g0 < min(G, (rank + 1) * per); g0 += 1024) {
+        u32 *const counter = cl.map_shared_rank(&s_n, 0);
+        const u32 per = (G + CUT_CL - 1) / CUT_CL, g_end = min(G, (rank + 1) * per);
+        for (u32 g0 = rank * per; g0 < g_end; g0 += 1024) {
             const u32 g = g0 + tid;
-            const bool in = g < min(G, (rank + 1) * per);
             float x = 0.0f;
             bool keep = false;
-            if (in) {
+            if (g < g_end) {
                 x = __fdiv_rn((float)stats[4 * g + 2 * which], (float)meta[g].y);
                 cp[g] = x;
                 keep = stats[4 * g + 3] > 0;
             }
             const u32 bal = __ballot_sync(FULL, keep);
-            if (lane == 0) s_warp[wid] = __popc(bal);
-            __syncthreads();
-            u32 wbase = 0, tot = 0;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) { const u32 t = s_warp[k]; if (k < (int)wid) wbase += t; tot += t; }
-            if (keep) *dsm_key(cl, s_keys, run + wbase + __popc(bal & LANE_LT(lane)), share_log) = __float_as_uint(x);
-            run += tot;
-            __syncthreads();
+            u32 base = 0;
+            if (lane == 0 && bal) base = atomicAdd(counter, (u32)__popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (keep) *dsm_key(cl, s_keys, base + __popc(bal & LANE_LT(lane)), share_log) = __float_as_uint(x);
         }
     }
+    cl.sync();
+    const u32 n = *cl.map_shared_rank(&s_n, 0);
     cl.sync();
     // bitonic sort, ascending (values are >= 0: u32 order == f32 order)
     for (u32 k = 2; k <= m; k <<= 1)
@@ -1270,74 +1296,104 @@ k_cut_sort_cluster(const u32 *__restrict__ stats, const uint4 *__restrict__ meta
         if (t < n) sorted[(size_t)which * G + t] = s_keys[o];
     }
     if (rank == 0) {
-        // P_0 = 0, P_k = P_{k-1} + v[n-k]: one thread, the values staged CUT_CHUNK at a time by the whole CTA
-        if (tid == 0) { s_carry = 0.0f; sc->n_members[which] = n; }
+        // P_0 = 0, P_k = P_{k-1} + v[n-k]: one thread, the values staged PREFIX_CHUNK at a time by the whole CTA.  Once k_cut_fold
+        // (running beside this kernel) has published the total, the chain ends with the first chunk whose last sum stops the loop
+        // of get_quantile_cut_off: k_cut_finish will not look further
+        if (tid == 0) { s_carry = 0.0f; s_stop = 0; sc->n_members[which] = n; }
         float *P = prefix + (size_t)which * G;
-        for (u32 k0 = 0; k0 < n; k0 += CUT_CHUNK) {                // P_{k0} .. P_{k0 + cn - 1}
-            const u32 cn = min((u32)CUT_CHUNK, n - k0);
-            // s_p[k] = v[n - (k0 + k)] for k >= 1 (the term that makes P_{k0+k} out of P_{k0+k-1}); s_p[0] pairs with the carry
+        u32 k_done = 0;
+        for (u32 k0 = 0; k0 < n; k0 += PREFIX_CHUNK) {             // P_{k0} .. P_{k0 + cn - 1}
+            const u32 cn = min((u32)PREFIX_CHUNK, n - k0);
+            // s_p[k] = v[n - (k0 + k)] for k0 + k >= 1 (the term that makes P_{k0+k} out of P_{k0+k-1}); P_0 = 0
             for (u32 k = tid; k < cn; k += 1024) {
                 const u32 kk = k0 + k;
                 s_p[k] = kk == 0 ? 0.0f : __uint_as_float(*dsm_key(cl, s_keys, n - kk, share_log));
             }
             __syncthreads();
             if (tid == 0) {
-                float run = s_carry;
-                u32 k = 0;
-                for (; k + 16 <= cn; k += 16) {
-                    float x[16];
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) x[t] = s_p[k + t];
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) { run = __fadd_rn(run, x[t]); s_p[k + t] = run; }
-                }
-                for (; k < cn; ++k) { run = __fadd_rn(run, s_p[k]); s_p[k] = run; }
+                const float run = running_sums_in_order(s_carry, s_p, cn);
                 s_carry = run;
+                if (*(volatile u32 *)&sc->tot_ready[which]) {
+                    __threadfence();
+                    if (!(__fdiv_rn(run, *(volatile float *)&sc->tot[which]) < q)) s_stop = 1;
+                }
             }
             __syncthreads();
             for (u32 k = tid; k < cn; k += 1024) P[k0 + k] = s_p[k];
+            k_done = k0 + cn;
+            if (s_stop) break;
             __syncthreads();
         }
+        if (tid == 0) sc->k_done[which] = k_done;
     }
     cl.sync();                                // nobody leaves while rank 0 may still read its share
 }
 
-// one CTA: both cut-offs by a parallel search over the running sums, then the valid set
+// Both cut-offs by a parallel search over the running sums (every CTA for itself: two rounds of 1024 probes, P_k / total < q is
+// monotone in k), then the valid set and the -v counters of the CTA's 1024 references
 __global__ void __launch_bounds__(1024)
 k_cut_finish(const u32 *__restrict__ stats, u32 G, float q, u32 min_reads, const float *__restrict__ cp_all, const u32 *__restrict__ sorted,
              const float *__restrict__ prefix, u32 *__restrict__ valid_bits, unsigned char *__restrict__ valid_bytes, DevScalars *sc)
 {
-    __shared__ u32 s_k[2];
+    __shared__ u32 s_k[2][2];
+    __shared__ float s_cut[2];
     const u32 tid = threadIdx.x;
     if (min_reads == 0) {                     // -mr default: 1 + (matches_count-1)/10000 (src/slimm.hpp:458-459)
         const u32 R = (u32)sc->n_reads;
         min_reads = R ? 1u + (R - 1u) / 10000u : 0u;
     }
     const u32 n = sc->n_members[0];
-    if (tid < 2) s_k[tid] = n ? n - 1 : 0;    // the loop also ends when i reaches 0, i.e. after n - 1 trips
+    const bool active = q < 1.0f && n > 0;
+    // i = n-1; while ((sub/total) < q && i > 0) { sub += v[i]; --i; }: after k trips sub == P_k; the loop also ends after n - 1 trips
+    if (tid < 4) s_k[tid >> 1][tid & 1] = n ? n - 1 : 0;
     __syncthreads();
-    if (q < 1.0f && n > 0) {
-        for (u32 which = 0; which < 2; ++which) {
-            const float total = sc->tot[which];
-            const float *P = prefix + (size_t)which * G;
-            // i = n-1; while ((sub/total) < q && i > 0) { sub += v[i]; --i; }: after k trips sub == P_k
-            u32 best = 0xFFFFFFFFu;
-            for (u32 k = tid; k < n; k += 1024)
-                if (!(__fdiv_rn(P[k], total) < q)) { best = k; break; }   // my smallest k that stops the loop (k ascends)
-            if (best != 0xFFFFFFFFu) atomicMin(&s_k[which], best);
+    if (active) {
+        const u32 stride = (n + 1023) / 1024;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {                  // round 1: every stride-th k (the running sums end at k_done: a stop lies before it, or k_done == n)
+            const u32 k = tid * stride;
+            if (k < sc->k_done[which] && !(__fdiv_rn(prefix[(size_t)which * G + k], sc->tot[which]) < q)) atomicMin(&s_k[which][0], k);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {                  // round 2: the stride before the first probe that stopped
+            const u32 hi = s_k[which][0];                          // the first probe that stopped, or n - 1: the first stop lies in (hi - stride, hi]
+            const u32 lo = hi >= stride ? hi - stride : 0u;
+            for (u32 k = lo + tid; k <= hi && k < sc->k_done[which]; k += 1024)
+                if (!(__fdiv_rn(prefix[(size_t)which * G + k], sc->tot[which]) < q)) { atomicMin(&s_k[which][1], k); break; }
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        float c0 = 0.0f, c1 = 0.0f;
-        if (q < 1.0f && n > 0) {
-            c0 = __uint_as_float(sorted[n - 1 - s_k[0]]);
-            c1 = __uint_as_float(sorted[(size_t)G + n - 1 - s_k[1]]);
-        }
-        sc->cut = c0; sc->ucut = c1;
-    }
+    if (tid < 2) s_cut[tid] = active ? __uint_as_float(sorted[(size_t)tid * G + n - 1 - s_k[tid][1]]) : 0.0f;
     __syncthreads();
-    cutoffs_valid_set(stats, G, min_reads, cp_all, valid_bits, valid_bytes, sc);
+    const float c0 = s_cut[0], c1 = s_cut[1];
+    if (blockIdx.x == 0 && tid == 0) { sc->cut = c0; sc->ucut = c1; }
+    // valid set + -v counters (src/slimm.hpp:354-378) of my 1024 references
+    const float *cpa = cp_all, *ucpa = cp_all + G;
+    const u32 g = blockIdx.x * 1024 + tid;
+    u32 nv = 0, fc = 0, fu = 0, fm = 0, rc = 0;
+    unsigned long long pairs = 0;
+    bool ok = false;
+    if (g < G) {
+        const u32 reads = stats[4 * g + 1];
+        if (reads > 0) {
+            rc = 1; pairs = reads;
+            const float a = cpa[g], b = ucpa[g];
+            ok = a >= c0 && b >= c1;
+            if (ok) nv = 1;
+            else { fu = b < c1; fm = reads < min_reads; fc = a < c0; }
+        }
+        valid_bytes[g] = ok;
+    }
+    const u32 word = __ballot_sync(FULL, ok);
+    if ((tid & 31) == 0 && g < G) valid_bits[g >> 5] = word;
+    nv = warp_sum(nv); fc = warp_sum(fc); fu = warp_sum(fu); fm = warp_sum(fm); rc = warp_sum(rc);
+    pairs = warp_sum64(pairs);
+    if ((tid & 31) == 0 && (rc | nv)) {
+        atomicAdd(&sc->n_valid, nv); atomicAdd(&sc->failed_cov, fc); atomicAdd(&sc->failed_ucov, fu);
+        atomicAdd(&sc->failed_minread, fm); atomicAdd(&sc->ref_count, rc);
+        atomicAdd(&sc->n_pairs, pairs);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -934,9 +934,9 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
             u32 m = CUT_CL * 1024;
             while (m < ctx->G) m <<= 1;
             const size_t dyn = (size_t)(m / CUT_CL) * 4;
-            k_cut_sort_cluster<<<2 * CUT_CL, 1024, dyn, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix, ctx->d_sc);
+            k_cut_sort_cluster<<<2 * CUT_CL, 1024, dyn, ctx->stream>>>(ctx->d_stats, ctx->d_meta, ctx->G, cov_cut_off, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix, ctx->d_sc);
             CU(cudaStreamWaitEvent(ctx->stream, ctx->fold_done, 0));
-            k_cut_finish<<<1, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix,
+            k_cut_finish<<<(ctx->G + 1023) / 1024, 1024, 0, ctx->stream>>>(ctx->d_stats, ctx->G, cov_cut_off, min_reads, ctx->d_cp, ctx->d_cut_sorted, ctx->d_cut_prefix,
                                                       ctx->d_valid_bits, ctx->d_valid_bytes, ctx->d_sc);
             ctx->launches += 2;
         } else {
