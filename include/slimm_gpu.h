@@ -157,6 +157,11 @@ int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
 int slimm_gpu_p2p_reserve(slimm_gpu_ctx *ctx, uint64_t cap_items, void *ipc_handle_64);
 int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles /* [n_ranks][64] */, uint32_t n_ranks);
 int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts /* [n_ranks][n_slices] */, uint64_t *n_recv);
+/* The same exchange planned on the device: d_all_counts is the all-gathered table of slimm_gpu_slice_counts_device (device memory,
+ * [n_ranks][n_slices]); no host copy of the counts, no synchronisation - coverage, the collectives and the split queue up on the
+ * stream.  A receive buffer that would overflow is reported by slimm_gpu_get_summary (SLIMM_GPU_ERANGE). */
+int slimm_gpu_slice_counts_device(slimm_gpu_ctx *ctx, void **d_counts, uint32_t *n_slices);
+int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_counts);
 int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx);
 /* back to the all-to-all exchange (e.g. when another rank could not map the buffers) */
 int slimm_gpu_p2p_disable(slimm_gpu_ctx *ctx);

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
     "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
     "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received", "slimm_gpu_p2p_disable",
+    "slimm_gpu_slice_counts_device", "slimm_gpu_split_to_peers_device",
 ]
 
 
@@ -126,6 +127,8 @@ def load_library():
     lib.slimm_gpu_p2p_connect.argtypes = [vp, vp, u32]
     lib.slimm_gpu_split_to_peers.argtypes = [vp, vp, C.POINTER(u64)]
     lib.slimm_gpu_accumulate_received.argtypes = [vp]
+    lib.slimm_gpu_slice_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u32)]
+    lib.slimm_gpu_split_to_peers_device.argtypes = [vp, vp]
     lib.slimm_gpu_p2p_disable.argtypes = [vp]
     lib.slimm_gpu_stats_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     lib.slimm_profile_db_is_tree_consistent.argtypes = [u32, vp, u64, vp, vp, vp, C.POINTER(C.c_int)]
@@ -293,6 +296,16 @@ class SlimmGpu:
         n = C.c_uint64(0)
         self._check(self._lib.slimm_gpu_split_to_peers(self._ctx, t.ctypes.data, C.byref(n)), "split_to_peers")
         return int(n.value)
+
+    def slice_counts_device(self) -> Tuple[int, int]:
+        """Device pointer to this rank's items per histogram slice (u32) and the number of slices."""
+        p, n = C.c_void_p(), C.c_uint32()
+        self._check(self._lib.slimm_gpu_slice_counts_device(self._ctx, C.byref(p), C.byref(n)), "slice_counts_device")
+        return p.value, n.value
+
+    def split_to_peers_device(self, all_counts_ptr: int):
+        """The peer-to-peer split planned on the device from the all-gathered counts ([n_ranks][n_slices] u32, device memory)."""
+        self._check(self._lib.slimm_gpu_split_to_peers_device(self._ctx, C.c_void_p(all_counts_ptr)), "split_to_peers_device")
 
     def p2p_disable(self):
         self._check(self._lib.slimm_gpu_p2p_disable(self._ctx), "p2p_disable")

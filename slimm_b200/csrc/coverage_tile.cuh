@@ -197,7 +197,7 @@ __device__ __forceinline__ void covt_step3(const Rec &rec, const CovParams &P, u
         for (int k = 0; k < 4; ++k)
             if ((keep4 >> k) & 1u) {
                 const bool head = (h5 >> k) & 1u;
-                cw_c[o] = g[k] | (head ? CW_HEAD : 0u);
+                cw_c[o] = (g[k] < P.G ? g[k] : 0u) | (head ? CW_HEAD : 0u);   // an id out of range is reported later; the word stays harmless
                 if (EXTRA && cwi_c) cwi_c[o] = base + k;
                 if (head) rs_c[q++] = o | ((u32)cnt[at + k] << 16);
                 ++o;
@@ -391,7 +391,7 @@ k_coverage_tile(const __grid_constant__ Rec rec, u32 n, const __grid_constant__ 
                 const u32 tk = __shfl_sync(FULL, tail_keep, __ffs(TB) - 1);
                 if ((tk >> lane) & 1u) {
                     const u32 o = out.n_cw + __popc(tk & LANE_LT(lane));
-                    cw_c[o] = sg[32 + COVT_T + lane];
+                    cw_c[o] = sg[32 + COVT_T + lane] < P.G ? sg[32 + COVT_T + lane] : 0u;
                     if (EXTRA && cwi_c) cwi_c[o] = t0 + COVT_T + lane;
                 }
                 out.n_cw += __popc(tk);

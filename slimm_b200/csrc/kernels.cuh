@@ -359,7 +359,7 @@ k_coverage(Rec rec, u32 n, CovParams P)
                 const u32 Hm = __ballot_sync(FULL, multi && is_head);
                 if (multi && first) {
                     const u32 local = n_cw + __popc(C & LANE_LT(lane));
-                    cw_c[local] = g | (is_head ? CW_HEAD : 0u);
+                    cw_c[local] = (ok ? g : 0u) | (is_head ? CW_HEAD : 0u);   // an id out of range is reported later; the word stays harmless
                     if (EXTRA && cwi_c) cwi_c[local] = p + lane;
                     if (is_head) rs_c[n_rs + __popc(Hm & LANE_LT(lane))] = local | ((u32)__popc(C & win.M) << 16);
                 }
@@ -518,6 +518,41 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
     }
 }
 
+// Where THIS rank's items of every slice go (sharded runs, peer-to-peer exchange), computed on the device from the all-gathered
+// slice counts, so that no host round trip sits between the coverage stage and the split: the receive buffer of owner q holds
+// its slices in ascending order, inside a slice the source ranks in ascending order (slimm_gpu_split_to_peers has the host twin).
+// One CTA of MAX_BUCKETS threads.
+__global__ void __launch_bounds__(MAX_BUCKETS)
+k_peer_dest(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32 n_slices, u32 n_ranks, u32 me, u32 *const *__restrict__ peer_recv /*[n_ranks]*/,
+            u64 recv_cap, u32 **__restrict__ dest /*[MAX_BUCKETS]*/, u32 *__restrict__ n_recv, u32 *__restrict__ overflow)
+{
+    __shared__ u32 s[MAX_BUCKETS + 1];
+    const u32 tid = threadIdx.x;
+    u32 tot = 0, before = 0;                   // items of slice tid from all ranks / from the ranks below me
+    if (tid < n_slices)
+        for (u32 src = 0; src < n_ranks; ++src) { const u32 c = all_counts[(size_t)src * n_slices + tid]; if (src < me) before += c; tot += c; }
+    s[tid + 1] = tot;
+    if (tid == 0) s[0] = 0;
+    __syncthreads();
+    for (u32 d = 1; d < MAX_BUCKETS; d <<= 1) {                    // inclusive scan of s[1..]
+        const u32 t = tid + 1 > d ? s[tid + 1 - d] : 0;
+        __syncthreads();
+        s[tid + 1] += t;
+        __syncthreads();
+    }
+    if (tid < n_slices) {
+        u32 q = 0;                                                 // owner of slice tid: slices [ns q / n, ns (q+1) / n)
+        while ((u64)n_slices * (q + 1) / n_ranks <= tid) ++q;
+        const u32 lo = (u32)((u64)n_slices * q / n_ranks);
+        dest[tid] = peer_recv[q] + (s[tid] - s[lo]) + before;
+    }
+    if (tid < n_ranks) {
+        const u32 lo = (u32)((u64)n_slices * tid / n_ranks), hi = (u32)((u64)n_slices * (tid + 1) / n_ranks);
+        if ((u64)(s[hi] - s[lo]) > recv_cap) atomicOr(overflow, 1u);
+        if (tid == me) *n_recv = s[hi] - s[lo];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 accumulate: applies the grouped items in stream order, one 64-bit RED each: the CTAs in flight work
 // on one or two adjacent histogram slices, so the REDs meet in L2 and a slice's sectors travel HBM -> L2 ->
@@ -571,10 +606,11 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 __device__ __forceinline__ u32 fine_base(u32 first_item, u32 cshift) { return ((first_item & 0x7FFFFFFFu) >> cshift) << (cshift - FINE_SHIFT); }
 
 __global__ void __launch_bounds__(256)
-k_fine_count(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_given, u32 cshift, u32 *__restrict__ fine_cnt)
+k_fine_count(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr /* number of items on the device, or null: n_given */, u32 n_given, u32 cshift,
+             u32 *__restrict__ fine_cnt)
 {
     __shared__ u32 s_cnt[FINE_REL];
-    const u32 n = sd ? sd->total_items : n_given;
+    const u32 n = n_ptr ? *n_ptr : n_given;
     const u32 tid = threadIdx.x;
     const u64 n_tiles = ((u64)n + FINE_TILE - 1) / FINE_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -637,14 +673,14 @@ k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u3
 }
 
 __global__ void __launch_bounds__(256)
-k_fine_split(const u32 *__restrict__ items, const Sched *__restrict__ sd, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
+k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
              u32 *__restrict__ out)
 {
     __shared__ u32 s_cnt[FINE_REL];            // items of each fine slice in this tile, then the slice's tile-local start
     __shared__ u32 s_delta[FINE_REL];          // global start - tile-local start (mod 2^32)
     __shared__ u32 s_item[FINE_TILE];
     __shared__ u32 s_warp_tot[8];
-    const u32 n = sd ? sd->total_items : n_given;
+    const u32 n = n_ptr ? *n_ptr : n_given;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 n_tiles = ((u64)n + FINE_TILE - 1) / FINE_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

@@ -79,7 +79,9 @@ struct slimm_gpu_ctx {
     u32 shard_rank = 0, shard_n = 1;        // histogram slices sharded over ranks (slimm_gpu_set_shard)
     // peer-to-peer item exchange: every rank's receive buffer is mapped into every other rank (CUDA IPC over NVLink)
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
-    u32 **d_dest = nullptr;
+    u32 **d_dest = nullptr; u32 **d_peer_recv = nullptr; u32 *d_n_recv = nullptr;   // d_n_recv[0]: items this rank receives, [1]: a receive buffer would overflow
+    bool n_recv_on_device = false;          // the split was planned on the device (slimm_gpu_split_to_peers_device): n_recv lives there
+    bool verify_pending = false;            // the optimistic checks of the coverage stage (ids non-decreasing, reference ids in range) have not been read back yet
     // fine slices: the histogram is accumulated in shared memory, 2^14 bins per CTA (k_fine_*)
     u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr, *d_fine_hot = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
     int acc_mode = 1;                       // 1: fine slices in shared memory, 0: 64-bit REDs into L2-resident slices
@@ -315,7 +317,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
-    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest);
+    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest); cudaFree(ctx->d_peer_recv); cudaFree(ctx->d_n_recv);
     cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref); cudaFree(ctx->d_fine_hot);
     for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
     cudaFree(ctx->d_recv);
@@ -417,7 +419,7 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
 // Accumulate + per-reference statistics in shared memory, fine slice by fine slice.  items: grouped by coarse slice
 // (their number is sd->total_items on the device, or n_given); n_cap bounds it on the host; out_buf receives the items
 // grouped by fine slice; [lo_bin, hi_bin) are the bins this rank owns.
-static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd, u64 n_given, u64 n_cap, u32 *out_buf, u64 lo_bin, u64 hi_bin)
+static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_ptr, u64 n_given, u64 n_cap, u32 *out_buf, u64 lo_bin, u64 hi_bin)
 {
     const u64 n_fine = (ctx->Bp + FINE_BINS - 1) >> FINE_SHIFT;
     if (ctx->fine_slices_cap < n_fine) {
@@ -434,13 +436,13 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const Sched *sd
     const u64 n_tiles = (n_cap + FINE_TILE - 1) / FINE_TILE;
     if (n_tiles) {
         const int cgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 8));
-        k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
+        k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
     }
     k_fine_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot,
                                              ctx->d_fine_cnt + n_fine + 1);
     if (n_tiles) {
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
-        k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, sd, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
+        k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
     }
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
@@ -565,7 +567,7 @@ static int launch_coverage_t(slimm_gpu_ctx *ctx, Rec rec)
         }
     }
     if (ctx->shard_n > 1) { CU(cudaGetLastError()); return SLIMM_GPU_OK; }   // the caller exchanges the items, then slimm_gpu_accumulate_items
-    if (ctx->acc_mode == 1) return fine_accumulate(ctx, ctx->d_grouped, ctx->d_sched, 0, n, ctx->d_items, 0, ctx->Bp);
+    if (ctx->acc_mode == 1) return fine_accumulate(ctx, ctx->d_grouped, &ctx->d_sched->total_items, 0, n, ctx->d_items, 0, ctx->Bp);
     {
         CU(cudaStreamWaitEvent(ctx->stream, ctx->zero_done, 0));   // the histogram was zero-filled on the side stream meanwhile
         TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
@@ -673,6 +675,34 @@ static int sort_records(slimm_gpu_ctx *ctx)
     return SLIMM_GPU_OK;
 }
 
+// Reads the flags the coverage stage left behind.  Input that was not grouped by read: the records are sorted on the device and
+// every stage that already ran is run again (the first pass was wasted, never wrong: nothing of it survives).
+static int verify_input(slimm_gpu_ctx *ctx)
+{
+    if (!ctx->verify_pending) return SLIMM_GPU_OK;
+    ctx->verify_pending = false;
+    CU(cudaSetDevice(ctx->device));
+    for (int pass = 0; pass < 2; ++pass) {
+        u32 flags = 0;
+        CU(cudaMemcpyAsync(&flags, &ctx->d_sc->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (flags & 2u) { ctx->stage = ST_CREATED; return fail(ctx, SLIMM_GPU_EINVAL, "a record references a contig id >= n_refs"); }
+        if (!(flags & 1u)) return SLIMM_GPU_OK;
+        if (pass == 1) return fail(ctx, SLIMM_GPU_ECUDA, "read ids still out of order after the device sort");
+        if (ctx->shard_n > 1) { ctx->stage = ST_CREATED; return fail(ctx, SLIMM_GPU_EINVAL, "a sharded run needs every rank's records grouped by read"); }
+        const int stage = ctx->stage;
+        ctx->was_sorted = false;
+        int rc = sort_records(ctx); if (rc) return rc;
+        ctx->stats_done = false; ctx->h_assign_ok = false; ctx->finished = false;
+        rc = zero_state(ctx); if (rc) return rc;
+        rc = launch_coverage(ctx); if (rc) return rc;
+        ctx->stage = ST_COVERAGE;
+        if (stage >= ST_FILTER) { rc = slimm_gpu_filter(ctx, ctx->q, ctx->min_reads_opt); if (rc) return rc; }
+        if (stage >= ST_ASSIGN) { rc = slimm_gpu_assign(ctx); if (rc) return rc; }
+    }
+    return SLIMM_GPU_OK;
+}
+
 int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
 {
     if (!ctx) return SLIMM_GPU_EINVAL;
@@ -683,23 +713,15 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
     CU(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
     for (int i = 0; i < SLIMM_GPU_T_COUNT; ++i) ctx->ev_used[i] = false;
     ctx->use_sorted = false; ctx->was_sorted = true; ctx->h_assign_ok = false; ctx->finished = false; ctx->shard_acc_done = false; ctx->stats_done = false;
+    ctx->verify_pending = false; ctx->n_recv_on_device = false;
     int rc = zero_state(ctx);
     if (rc) return rc;
     if (ctx->n) {
         rc = launch_coverage(ctx);
         if (rc) return rc;
-        // optimistic: the kernel assumed non-decreasing read ids and verified it on the fly
-        u32 flags = 0;
-        CU(cudaMemcpyAsync(&flags, &ctx->d_sc->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (flags & 2u) return fail(ctx, SLIMM_GPU_EINVAL, "a record references a contig id >= n_refs");
-        if (flags & 1u) {
-            ctx->was_sorted = false;
-            rc = sort_records(ctx); if (rc) return rc;
-            rc = zero_state(ctx); if (rc) return rc;
-            rc = launch_coverage(ctx);
-            if (rc) return rc;
-        }
+        // optimistic: the kernel assumes non-decreasing read ids and reference ids in range and verifies both on the fly; the flags
+        // are read back with the first result (verify_input), so the stages queue up behind each other without a host round trip
+        ctx->verify_pending = true;
     }
     else if (ctx->shard_n > 1) CU(cudaMemsetAsync(ctx->d_sched, 0, sizeof(Sched), ctx->stream));   // no records on this rank: no items
     ctx->stage = ST_COVERAGE;
@@ -744,6 +766,7 @@ int slimm_gpu_get_slice_counts(slimm_gpu_ctx *ctx, uint32_t *counts, uint32_t ca
     if (!ctx || !n_slices) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_COVERAGE || !ctx->used_bucket) return fail(ctx, SLIMM_GPU_ESTATE, "slice counts exist after a bucketed coverage stage");
     CU(cudaSetDevice(ctx->device));
+    if (counts) { int rc = verify_input(ctx); if (rc) return rc; }
     const u32 ns = n_slices_of(ctx);
     *n_slices = ns;
     if (counts) {
@@ -751,6 +774,15 @@ int slimm_gpu_get_slice_counts(slimm_gpu_ctx *ctx, uint32_t *counts, uint32_t ca
         CU(cudaMemcpyAsync(counts, reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count), (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_slice_counts_device(slimm_gpu_ctx *ctx, void **d_counts, uint32_t *n_slices)
+{
+    if (!ctx || !d_counts || !n_slices) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->used_bucket) return fail(ctx, SLIMM_GPU_ESTATE, "slice counts exist after a bucketed coverage stage");
+    *d_counts = reinterpret_cast<char *>(ctx->d_sched) + offsetof(Sched, count);
+    *n_slices = n_slices_of(ctx);
     return SLIMM_GPU_OK;
 }
 
@@ -781,7 +813,7 @@ static int accumulate_owned(slimm_gpu_ctx *ctx, const u32 *d_items, u64 n_items)
             CU(cudaMalloc(&ctx->d_fine, std::max<u64>(n_items + n_items / 8, 1024) * 4));
             ctx->fine_cap = n_items + n_items / 8;
         }
-        int rc = fine_accumulate(ctx, d_items, nullptr, n_items, n_items, ctx->d_fine, lo_bin, hi_bin);
+        int rc = fine_accumulate(ctx, d_items, ctx->n_recv_on_device && d_items == ctx->d_recv ? ctx->d_n_recv : nullptr, n_items, n_items, ctx->d_fine, lo_bin, hi_bin);
         if (rc) return rc;
         ctx->shard_acc_done = true;
         return SLIMM_GPU_OK;
@@ -842,6 +874,10 @@ int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles, uint32_t 
         ctx->peer_recv[q] = (u32 *)p;
     }
     if (!ctx->d_dest) CU(cudaMalloc(&ctx->d_dest, MAX_BUCKETS * sizeof(u32 *)));
+    if (!ctx->d_n_recv) CU(cudaMalloc(&ctx->d_n_recv, 8));
+    cudaFree(ctx->d_peer_recv); ctx->d_peer_recv = nullptr;
+    CU(cudaMalloc(&ctx->d_peer_recv, n_ranks * sizeof(u32 *)));
+    CU(cudaMemcpy(ctx->d_peer_recv, ctx->peer_recv.data(), n_ranks * sizeof(u32 *), cudaMemcpyHostToDevice));
     ctx->p2p = true;
     return SLIMM_GPU_OK;
 }
@@ -889,6 +925,29 @@ int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts, uin
         CU(cudaStreamSynchronize(ctx->stream));   // dest is a host vector; and the caller's barrier comes next anyway
         ctx->split_pending = false;
     }
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_counts)
+{
+    if (!ctx || !d_all_counts) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_COVERAGE || !ctx->p2p) return fail(ctx, SLIMM_GPU_ESTATE, "split_to_peers belongs to a peer-to-peer sharded run, after coverage");
+    CU(cudaSetDevice(ctx->device));
+    const u32 ns = n_slices_of(ctx);
+    TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);
+    CU(cudaMemsetAsync(ctx->d_n_recv, 0, 8, ctx->stream));
+    k_peer_dest<<<1, MAX_BUCKETS, 0, ctx->stream>>>(d_all_counts, ns, ctx->shard_n, ctx->shard_rank, ctx->d_peer_recv, ctx->recv_cap, ctx->d_dest, ctx->d_n_recv,
+                                                    ctx->d_n_recv + 1);
+    ctx->launches++;
+    ctx->n_recv_on_device = true;
+    ctx->n_recv = ctx->recv_cap;              // an upper bound for the host side (buffers, grids); the kernels read the count on the device
+    if (ctx->split_pending) {
+        const u32 n = (u32)ctx->n;
+        launch_k_split<true>(ctx, 0, ctx->d_items, n, ctx->bucket_shift, ns, nullptr, ctx->d_dest);
+        ctx->launches++;
+        ctx->split_pending = false;
+    }
+    CU(cudaGetLastError());
     return SLIMM_GPU_OK;
 }
 
@@ -1027,7 +1086,9 @@ int slimm_gpu_run(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
     if (rc) return rc;
     rc = slimm_gpu_filter(ctx, cov_cut_off, min_reads);
     if (rc) return rc;
-    return slimm_gpu_assign(ctx);
+    rc = slimm_gpu_assign(ctx);
+    if (rc) return rc;
+    return verify_input(ctx);
 }
 
 // ---- results -----------------------------------------------------------------------------------
@@ -1036,10 +1097,14 @@ int slimm_gpu_get_summary(slimm_gpu_ctx *ctx, slimm_gpu_summary *out)
     if (!ctx || !out) return SLIMM_GPU_EINVAL;
     if (ctx->stage < ST_COVERAGE) return fail(ctx, SLIMM_GPU_ESTATE, "nothing has run yet");
     CU(cudaSetDevice(ctx->device));
+    { int rc = verify_input(ctx); if (rc) return rc; }
     { int rc = finish_assign(ctx); if (rc) return rc; }
     DevScalars s;
     CU(cudaMemcpyAsync(&s, ctx->d_sc, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
+    u32 nrecv[2] = {0, 0};
+    if (ctx->n_recv_on_device) CU(cudaMemcpyAsync(nrecv, ctx->d_n_recv, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (nrecv[1]) return fail(ctx, SLIMM_GPU_ERANGE, "a rank received more items than slimm_gpu_p2p_reserve reserved");
     memset(out, 0, sizeof *out);
     out->hits_count = (u32)(ctx->have_global_hits ? ctx->global_hits : ctx->n);
     out->matches_count = (u32)s.n_reads; out->uniq_matches_count = (u32)s.n_uniq; out->uniq_matches_count2 = (u32)s.n_uniq2;
@@ -1053,6 +1118,7 @@ int slimm_gpu_get_summary(slimm_gpu_ctx *ctx, slimm_gpu_summary *out)
 
 static int fetch_assign(slimm_gpu_ctx *ctx)
 {
+    { int rc = verify_input(ctx); if (rc) return rc; }
     if (ctx->h_assign_ok) return SLIMM_GPU_OK;
     if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
     CU(cudaSetDevice(ctx->device));
@@ -1070,6 +1136,7 @@ int slimm_gpu_get_ref_stats(slimm_gpu_ctx *ctx, uint32_t *reads_count, uint32_t 
     if (!ctx) return SLIMM_GPU_EINVAL;
     if (ctx->stage < ST_FILTER) return fail(ctx, SLIMM_GPU_ESTATE, "filter has not run");
     CU(cudaSetDevice(ctx->device));
+    { int rc = verify_input(ctx); if (rc) return rc; }
     const u32 G = ctx->G;
     std::vector<u32> st((size_t)G * 4);
     std::vector<float> cp((size_t)G * 2);
@@ -1144,6 +1211,13 @@ int slimm_gpu_fetch_bins(slimm_gpu_ctx *ctx, int which, uint32_t ref, uint32_t *
     if (which == 2 && !ctx->d_cov2) return fail(ctx, SLIMM_GPU_EINVAL, "uniq_cov2 needs SLIMM_GPU_KEEP_UNIQ_COV2");
     if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && ctx->used_bucket && ctx->acc_mode == 1) return fail(ctx, SLIMM_GPU_EINVAL, "the bins were not kept (SLIMM_GPU_SKIP_BINS)");
     CU(cudaSetDevice(ctx->device));
+    { int rc = verify_input(ctx); if (rc) return rc; }
+    if (ctx->shard_n > 1) {   // a sharded run keeps the bins of the slices this rank owns only (the others were never written)
+        u64 lo_bin = 0, hi_bin = 0;
+        owned_bins(ctx, &lo_bin, &hi_bin);
+        const u64 a = ctx->h_off[ref], b = a + ctx->h_len[ref] / ctx->w + 1u;
+        if (a < lo_bin || b > hi_bin) return fail(ctx, SLIMM_GPU_ESTATE, "sharded run: the bins of this reference live on the rank that owns its histogram slices");
+    }
     const u32 nb = ctx->h_len[ref] / ctx->w + 1u;
     if (cap < nb) return fail(ctx, SLIMM_GPU_EINVAL, "output buffer smaller than the number of bins");
     if (ctx->tmp_bins_cap < nb) {
@@ -1165,6 +1239,7 @@ int slimm_gpu_get_uniq2_nz(slimm_gpu_ctx *ctx, uint32_t *out)
     if (!ctx->d_cov2) return fail(ctx, SLIMM_GPU_EINVAL, "uniq_cov2 needs SLIMM_GPU_KEEP_UNIQ_COV2");
     if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
     CU(cudaSetDevice(ctx->device));
+    { int rc = verify_input(ctx); if (rc) return rc; }
     u32 *d_out = nullptr;
     CU(cudaMalloc(&d_out, (size_t)ctx->G * 4));
     k_cov2_nz<<<(ctx->G * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cov2, ctx->d_off, ctx->d_meta, ctx->G, d_out);
@@ -1182,6 +1257,7 @@ int slimm_gpu_read_results(slimm_gpu_ctx *ctx, uint32_t *read_id, uint8_t *kind,
     if (!(ctx->flags & SLIMM_GPU_READ_RESULTS)) return fail(ctx, SLIMM_GPU_EINVAL, "needs SLIMM_GPU_READ_RESULTS");
     if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
     CU(cudaSetDevice(ctx->device));
+    { int rc = verify_input(ctx); if (rc) return rc; }
     const u64 N = ctx->n;
     std::vector<unsigned char> k(N);
     std::vector<u32> v(N), r(N);
@@ -1238,6 +1314,7 @@ int slimm_gpu_profile(slimm_gpu_ctx *ctx, uint32_t rank, float abundance_cut_off
     if (!ctx->plan) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_set_taxa has not been called");
     if (ctx->stage < ST_ASSIGN) return fail(ctx, SLIMM_GPU_ESTATE, "assign has not run");
     if (rank < 1 || rank > 6) return fail(ctx, SLIMM_GPU_EINVAL, "rank must be 1 (species) .. 6 (phylum)");
+    { int rc = verify_input(ctx); if (rc) return rc; }
     if (ctx->plan->consistent && ctx->tail_mode != 1) {
         // K7: per-rank segmented reduction on the device, only the per-taxon aggregates of two ranks come back
         CU(cudaSetDevice(ctx->device));

@@ -66,6 +66,7 @@ def exchange_items(items, slice_counts: Sequence[int], group=None):
 
 
 _tokens = {}
+_tables = {}
 
 
 def _barrier_token(device):
@@ -125,19 +126,25 @@ def run_sharded(gpu, device, cov_cut_off: float, min_reads: int, global_hits: in
 
     mark("start")
     gpu.coverage()
-    counts = gpu.slice_counts()
     if getattr(gpu, "p2p", False):
-        # the split writes every item straight into its owner's receive buffer (peer memory over NVLink)
+        # the split writes every item straight into its owner's receive buffer (peer memory over NVLink).  Nothing here waits
+        # for the GPU: the slice counts are all-gathered on the device, a small kernel turns the table into destinations, and
+        # coverage, collectives and split queue up on the stream
         n_ranks = dist.get_world_size(group)
-        mine = torch.from_numpy(counts.astype(np.int32)).to(device)
-        table = torch.empty((n_ranks, mine.numel()), dtype=torch.int32, device=device)
+        p, ns = gpu.slice_counts_device()
+        mine = api.device_tensor(p, ns, torch.int32, device)
+        key = (id(gpu), n_ranks, ns)
+        table = _tables.get(key)
+        if table is None:
+            table = _tables[key] = torch.empty((n_ranks, ns), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(table, mine, group=group)
         mark("coverage")
-        gpu.split_to_peers(table.cpu().numpy().view(np.uint32))
+        gpu.split_to_peers_device(table.data_ptr())
         dist.all_reduce(_barrier_token(device), group=group)       # every rank's stores have landed before anyone accumulates
         mark("split into peers")
         gpu.accumulate_received()
     else:
+        counts = gpu.slice_counts()
         n_items = int(counts.sum(dtype=np.int64))
         items = api.device_tensor(gpu.items_device(), max(n_items, 1), torch.int32, device)[:n_items]
         mark("coverage+split")
