@@ -16,10 +16,10 @@ from slimm_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
-def _community(G, seed, len_lo=1_000_000, len_hi=6_000_000):
+def _community(G, seed, len_lo=1_000_000, len_hi=6_000_000, sigma=2.0):
     rng = np.random.default_rng(seed)
     tax, accs = synth.make_taxonomy(G)
-    contigs = synth.make_contigs(G, rng, accs, len_lo, len_hi)
+    contigs = synth.make_contigs(G, rng, accs, len_lo, len_hi, sigma=sigma)
     db = synth.database_for(tax)
     lineage = db.lineage_table(contigs.accessions)
     return rng, contigs, db, lineage
@@ -77,7 +77,7 @@ def test_cfg5_shaped_fine_bins():
     import torch
     from slimm_b200 import synth_torch
     G, N, w = 8000, 40_000_000, 100
-    rng, contigs, db, lineage = _community(G, 777)
+    rng, contigs, db, lineage = _community(G, 777, sigma=3.5)     # a long tail of references nobody maps to: empty fine slices
     dev = torch.device("cuda", 0)
     recs = synth_torch.make_records_device(contigs.lengths, contigs.weights, N, dev, seed=4711, multi_frac=0.2, k_lo=2, k_hi=8, neigh=8)
     rid = recs.read_id.cpu().numpy().view(np.uint32)
