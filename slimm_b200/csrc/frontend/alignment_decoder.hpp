@@ -460,11 +460,22 @@ public:
             }
         });
         std::string frame_err;
+        std::atomic<bool> stop(false);                        // the consumer gave up (not grouped, parse error, sink error): stop reading and inflating
         std::thread framer([&] {
             std::unique_ptr<ChunkReader> rd = make_reader(file_, comp_, CHUNK, n_inflate);
-            frame(*rd, [&](ParseJob &job) { parse.push(std::move(job)); return true; }, frame_err, 0);
+            frame(*rd, [&](ParseJob &job) {
+                if (stop.load(std::memory_order_relaxed)) return false;
+                parse.push(std::move(job));
+                return !stop.load(std::memory_order_relaxed);
+            }, frame_err, 0);
             parse.close();
         });
+        // the framer is joined on every way out of this function, exceptions of the sink included (a joinable std::thread that is
+        // destroyed ends the process)
+        struct JoinGuard {
+            std::thread &t; std::atomic<bool> &stop; decltype(parse) &stage;
+            ~JoinGuard() { if (t.joinable()) { stop.store(true); stage.abort(); t.join(); } }
+        } guard{framer, stop, parse};
         RecordBatch batch = first;
         ReadIdTable table;
         std::string prev_key;
@@ -522,7 +533,7 @@ public:
             st.records_kept += n;
         }
         if (ok && assume_grouped && came_back.load()) { st.not_grouped = true; ok = false; }   // every worker is done by now
-        if (!ok) parse.abort();
+        if (!ok) { stop.store(true); parse.abort(); }
         framer.join();
         if (ok && !frame_err.empty()) { err = frame_err; ok = false; }
         if (ok && batch.n) sink(batch);

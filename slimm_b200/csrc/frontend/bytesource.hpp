@@ -185,6 +185,8 @@ private:
             if (bs < 26 || off + bs > f_.n) { g.error = "truncated or corrupt BGZF block"; break; }
             const size_t xlen = le16(f_.p + off + 10);
             const size_t isize = le32(f_.p + off + bs - 4);
+            // the deflate payload must fit between the extra field and the trailer; a BGZF block inflates to at most 64 KiB
+            if (bs < 12 + xlen + 8 || isize > 65536) { g.error = "truncated or corrupt BGZF block"; break; }
             g.blocks.push_back(Block{off + 12 + xlen, bs - 12 - xlen - 8, g.out_len, isize});
             g.out_len += isize;
             off += bs;

@@ -271,7 +271,119 @@ def case_adeno():
         run_ref(cd, "default", os.path.join(cd, "db.sldb"), src, [], True)
 
 
-CASES = {"quirk": case_quirk, "dup": case_dup, "synth1k": case_synth1k, "synth1k_shuffled": case_synth1k_shuffled,
+
+# --------------------------------------------------------------------------------------------
+# Config 1 of BASELINE.json: a REAL mapper's output (record order, flags, secondary-hit layout, strain-level
+# multi-mapping) - reads sampled from the reference's own tests/example/toy-references.fa, mapped with yara (vendored with
+# the reference under include/seqan/apps/yara; built per SURVEY.md Appendix B into $YARA_DIR, default /tmp/yara).
+TOY_TAXA = [  # accession -> (strain name, species, genus, family, order, class, phylum)
+    ("CP009656", "Borrelia burgdorferi B31", "Borrelia burgdorferi", "Borrelia", "Spirochaetaceae", "Spirochaetales", "Spirochaetia", "Spirochaetes"),
+    ("CP007793", "Azospirillum brasilense Az39", "Azospirillum brasilense", "Azospirillum", "Rhodospirillaceae", "Rhodospirillales", "Alphaproteobacteria", "Proteobacteria"),
+    ("CP007604", "Helicobacter pylori BM013A", "Helicobacter pylori", "Helicobacter", "Helicobacteraceae", "Campylobacterales", "Epsilonproteobacteria", "Proteobacteria"),
+    ("CP007605", "Helicobacter pylori BM012B", "Helicobacter pylori", "Helicobacter", "Helicobacteraceae", "Campylobacterales", "Epsilonproteobacteria", "Proteobacteria"),
+    ("CP007606", "Helicobacter pylori BM013B", "Helicobacter pylori", "Helicobacter", "Helicobacteraceae", "Campylobacterales", "Epsilonproteobacteria", "Proteobacteria"),
+    ("AP014622", "Pseudomonas aeruginosa NCGM 1900", "Pseudomonas aeruginosa", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("AP014646", "Pseudomonas aeruginosa NCGM 1984", "Pseudomonas aeruginosa", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("CP008896", "Pseudomonas fluorescens UK4", "Pseudomonas fluorescens", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("AJ344068", "Pseudomonas putida pWW0", "Pseudomonas putida", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("CP007620", "Pseudomonas putida DLL-E4", "Pseudomonas putida", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("CP007441", "Pseudomonas stutzeri 28a24", "Pseudomonas stutzeri", "Pseudomonas", "Pseudomonadaceae", "Pseudomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("AM920689", "Xanthomonas campestris B100", "Xanthomonas campestris", "Xanthomonas", "Xanthomonadaceae", "Xanthomonadales", "Gammaproteobacteria", "Proteobacteria"),
+    ("EU186381", "Agrobacterium rhizogenes pRi2659", "Agrobacterium rhizogenes", "Agrobacterium", "Rhizobiaceae", "Rhizobiales", "Alphaproteobacteria", "Proteobacteria"),
+    ("CP009144", "Sinorhizobium meliloti RMO17", "Sinorhizobium meliloti", "Sinorhizobium", "Rhizobiaceae", "Rhizobiales", "Alphaproteobacteria", "Proteobacteria"),
+]
+
+
+def case_toy_yara():
+    import re
+    yara = os.environ.get("YARA_DIR", "/tmp/yara")
+    src = f"{REFERENCE}/tests/example/toy-references.fa"
+    if not (os.path.exists(os.path.join(yara, "yara_mapper")) and os.path.exists(os.path.join(yara, "yara_indexer")) and os.path.exists(src)):
+        print("skip toy_yara (needs yara_indexer / yara_mapper in $YARA_DIR, see SURVEY.md Appendix B)")
+        return
+    cd = os.path.join(GOLD, "toy_yara")
+    # references: header -> "ACC.V text" (the accession must lead the name, src/misc.hpp:415-422)
+    names, seqs, cur = [], [], []
+    for line in open(src):
+        if line.startswith(">"):
+            if cur:
+                seqs.append("".join(cur)); cur = []
+            names.append(re.sub(r"^>gi\|[0-9]+\|[a-z]+\|([A-Z0-9_]+\.[0-9]+)\| ", r"\1 ", line.strip()))
+        else:
+            cur.append(line.strip().upper())
+    seqs.append("".join(cur))
+    assert len(names) == len(TOY_TAXA) == 14
+    # taxonomy with all seven ranks for every genome (LCA = 0 reads cannot be pinned otherwise)
+    nodes = {1: (1, "no rank"), 2: (1, "superkingdom")}
+    tnames = {1: "root", 2: "Bacteria"}
+    ids = {}
+
+    def node(name, rank, parent):
+        if (name, rank) not in ids:
+            ids[(name, rank)] = 100 + len(ids)
+            nodes[ids[(name, rank)]] = (parent, rank)
+            tnames[ids[(name, rank)]] = name
+        return ids[(name, rank)]
+
+    acc_taxid = {}
+    for acc, strain, species, genus, family, order, cls, phylum in TOY_TAXA:
+        p = node(phylum, "phylum", 2); c = node(cls, "class", p); o = node(order, "order", c); f = node(family, "family", o)
+        g = node(genus, "genus", f); sp = node(species, "species", g); st = node(strain, "no rank", sp)
+        acc_taxid[acc] = st
+    tax = synth.Taxonomy(nodes, tnames, acc_taxid)
+    sn = [n.split(" ")[0] for n in names]
+    contigs = synth.Contigs(sn, [x.split(".")[0] for x in sn], np.asarray([len(x) for x in seqs], dtype=np.uint32),
+                            np.ones(14) / 14)
+    rng = np.random.default_rng(20261018)
+    comp = str.maketrans("ACGTN", "TGCAN")
+    with tempfile.TemporaryDirectory() as td:
+        ref_fa = os.path.join(td, "refs.fa")
+        with open(ref_fa, "w") as f:
+            for n, sq in zip(names, seqs):
+                f.write(">" + n + "\n")
+                for i in range(0, len(sq), 70):
+                    f.write(sq[i:i + 70] + "\n")
+        # 20 000 reads of 100 bp, genome ~ length, 1 % substitutions, half of them reverse-complemented, non-ACGT -> N
+        total = sum(len(x) for x in seqs)
+        with open(os.path.join(td, "reads.fa"), "w") as f:
+            for r in range(20000):
+                g = int(rng.choice(14, p=[len(x) / total for x in seqs]))
+                s0 = int(rng.integers(0, len(seqs[g]) - 100))
+                read = list(re.sub("[^ACGT]", "N", seqs[g][s0:s0 + 100]))
+                for k in np.nonzero(rng.random(100) < 0.01)[0]:
+                    read[k] = "ACGT"[int(rng.integers(0, 4))]
+                read = "".join(read)
+                if rng.random() < 0.5:
+                    read = read.translate(comp)[::-1]
+                f.write(f">read{r}\n{read}\n")
+        subprocess.run([os.path.join(yara, "yara_indexer"), ref_fa, "-o", os.path.join(td, "idx")], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([os.path.join(yara, "yara_mapper"), os.path.join(td, "idx"), os.path.join(td, "reads.fa"), "-sa", "record",
+                        "-s", "2", "-t", "4", "-o", os.path.join(td, "mapped.sam")], check=True, stdout=subprocess.DEVNULL)
+        # keep the mapper's records, order and flags; SEQ / QUAL only on the first 200 records (the reference samples the average
+        # read length from records that carry a SEQ, src/misc.hpp:509-522) so that the fixture stays small
+        sam = os.path.join(td, "in.sam")
+        n = 0
+        with open(os.path.join(td, "mapped.sam")) as f, open(sam, "w") as out:
+            for line in f:
+                if line.startswith("@"):
+                    out.write(line); continue
+                fl = line.rstrip("\n").split("\t")
+                n += 1
+                if n > 200:
+                    fl[9] = "*"; fl[10] = "*"
+                out.write("\t".join(fl[:11]) + "\n")      # optional tags dropped
+        fx, seqlen = _parse_sam(sam)
+        rec = synth.records_from_sam_fixture(fx)
+        db, db_path = db_via_reference(tax, contigs, cd)
+        save_case(cd, rec, contigs, db, _avg_len(seqlen), sam)
+        json.dump({"source": "reads sampled from tests/example/toy-references.fa, mapped with the vendored yara (SURVEY.md Appendix B)",
+                   "n_records_in_file": len(fx.qname), "kept_records": int(rec.read_id.size), "reads": int(rec.n_reads)},
+                  open(os.path.join(cd, "source.json"), "w"))
+        run_ref(cd, "default", db_path, sam, [], True)
+        run_ref(cd, "cc050_genus", db_path, sam, ["-cc", "0.5", "-r", "genus"], False)
+        run_ref(cd, "w1000", db_path, sam, ["-w", "1000"], False)
+
+CASES = {"toy_yara": case_toy_yara, "quirk": case_quirk, "dup": case_dup, "synth1k": case_synth1k, "synth1k_shuffled": case_synth1k_shuffled,
          "lca64": case_lca64, "missing": case_missing, "adeno": case_adeno}
 
 if __name__ == "__main__":

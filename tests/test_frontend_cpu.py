@@ -163,3 +163,28 @@ def test_command_line_errors(args, code, needle):
     r = subprocess.run([CLI] + args, capture_output=True, text=True)
     assert r.returncode == code
     assert needle in r.stderr + r.stdout
+
+
+def test_fallback_to_the_name_table_stops_the_first_pass_at_once(tmp_path):
+    """A read name that comes back early in a long gzipped SAM (the usual non-grouped input is a coordinate-sorted file): the
+    grouped-input attempt must stop reading and inflating there, not run to the end of the file, so the default costs about
+    one pass - not the two it cost while the framer kept going after the consumer had given up."""
+    import time
+    n = 700_000
+    lines = ["@SQ\tSN:c1\tLN:1000000"]
+    lines += [f"r{i}\t0\tc1\t{1 + i % 900000}\t60\t100M\t*\t0\t0\t{'ACGT' * 25}\t{'I' * 100}" for i in range(n)]
+    lines.insert(3, "r0\t256\tc1\t77\t60\t100M\t*\t0\t0\t*\t*")      # the third record repeats the first one's name
+    p = tmp_path / "in.sam.gz"
+    p.write_bytes(gzip.compress(("\n".join(lines) + "\n").encode(), 1))
+
+    def best(extra):
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            d = decode(p, tmp_path, 4, extra=extra)
+            t.append(time.perf_counter() - t0)
+            assert d["N"] == n + 1 and d["n_reads"] == n
+        return min(t)
+
+    exact, default = best(("--exact-ids",)), best(())
+    assert default < 1.45 * exact + 0.25, (default, exact)
