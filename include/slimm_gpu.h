@@ -109,6 +109,13 @@ int slimm_gpu_push(slimm_gpu_ctx *ctx, const uint32_t *read_id, const uint32_t *
                    const int32_t *begin_pos, uint64_t n);
 int slimm_gpu_push_device(slimm_gpu_ctx *ctx, const uint32_t *d_read_id, const uint32_t *d_ref_id,
                           const int32_t *d_begin_pos, uint64_t n);
+/* The same ingest in the 6.125-byte wire format of input GROUPED BY READ (what mappers write; the decoder knows after its own
+ * run check): instead of a 32-bit read id one bit per record - bit i%32 of word i/32 set when record i starts a new read - and
+ * the reference id as 16 bits (fewer than 65 536 contigs).  The dense read ids are rebuilt on the device (a running count of the
+ * set bits, continued across calls), so the PCIe link carries half the bytes of slimm_gpu_push.  The first record of a sample
+ * must have its bit set.  Calls may be mixed with slimm_gpu_push only in whole samples (SLIMM_GPU_ESTATE otherwise). */
+int slimm_gpu_push_packed(slimm_gpu_ctx *ctx, const uint32_t *new_read_bits, const uint16_t *ref_id16,
+                          const int32_t *begin_pos, uint64_t n);
 int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx);
 
 /* Stage 1 - coverage.  Replaces the per-read loop of analyze_alignments (src/slimm.hpp:219-257,

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "slimm_profile_db_is_tree_consistent", "slimm_gpu_set_shard", "slimm_gpu_get_slice_counts", "slimm_gpu_items_device",
     "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
     "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received", "slimm_gpu_p2p_disable",
-    "slimm_gpu_slice_counts_device", "slimm_gpu_split_to_peers_device",
+    "slimm_gpu_slice_counts_device", "slimm_gpu_split_to_peers_device", "slimm_gpu_push_packed",
 ]
 
 
@@ -95,6 +95,7 @@ def load_library():
     lib.slimm_gpu_host_free.argtypes = [vp]
     lib.slimm_gpu_push.argtypes = [vp, vp, vp, vp, u64]
     lib.slimm_gpu_push_device.argtypes = [vp, vp, vp, vp, u64]
+    lib.slimm_gpu_push_packed.argtypes = [vp, vp, vp, vp, u64]
     lib.slimm_gpu_sync_uploads.argtypes = [vp]
     lib.slimm_gpu_coverage.argtypes = [vp]
     lib.slimm_gpu_bins_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
@@ -220,6 +221,20 @@ class SlimmGpu:
 
     def push_ptrs(self, read_id_ptr: int, ref_id_ptr: int, begin_pos_ptr: int, n: int):
         self._check(self._lib.slimm_gpu_push(self._ctx, read_id_ptr, ref_id_ptr, begin_pos_ptr, n), "push")
+
+    def push_packed(self, new_read_bits, ref_id16, begin_pos):
+        """Grouped input in the 6.125-byte wire format (include/slimm_gpu.h): one "new read" bit, a 16-bit reference id and
+        the position per record."""
+        a = np.ascontiguousarray(new_read_bits, dtype=np.uint32)
+        b = np.ascontiguousarray(ref_id16, dtype=np.uint16)
+        c = np.ascontiguousarray(begin_pos, dtype=np.int32)
+        if b.size != c.size or a.size * 32 < b.size:
+            raise ValueError("record arrays differ in length")
+        self._keep += [a, b, c]
+        self._check(self._lib.slimm_gpu_push_packed(self._ctx, a.ctypes.data, b.ctypes.data, c.ctypes.data, b.size), "push_packed")
+
+    def push_packed_ptrs(self, bits_ptr: int, ref16_ptr: int, begin_pos_ptr: int, n: int):
+        self._check(self._lib.slimm_gpu_push_packed(self._ctx, bits_ptr, ref16_ptr, begin_pos_ptr, n), "push_packed")
 
     def push_device(self, read_id_ptr: int, ref_id_ptr: int, begin_pos_ptr: int, n: int):
         self._check(self._lib.slimm_gpu_push_device(self._ctx, read_id_ptr, ref_id_ptr, begin_pos_ptr, n), "push_device")

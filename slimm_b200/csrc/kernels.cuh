@@ -1749,6 +1749,75 @@ __global__ void k_finish_assign(u32 *__restrict__ uniq2, const u32 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// slimm_gpu_push_packed: the wire format of grouped input (one "new read" bit + a 16-bit reference id per record) back to
+// the struct of arrays the kernels read.  read_id[i] = id_base + (set bits among records 0..i) - 1.
+//   k_unpack_count   set bits per 1024-record tile
+//   k_unpack_scan    exclusive scan of the tile counts (one CTA), continued from / written back to the running id counter
+//   k_unpack_write   a warp per tile: word j of the tile is broadcast, lane l writes record 32 j + l (coalesced)
+// ------------------------------------------------------------------------------------------------
+#define UNPACK_TILE 1024u
+__global__ void k_unpack_count(const u32 *__restrict__ bits, u64 n, u32 *__restrict__ tile_cnt)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 tile = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_tiles = (n + UNPACK_TILE - 1) / UNPACK_TILE;
+    if (tile >= n_tiles) return;
+    const u64 i0 = tile * UNPACK_TILE + 32ull * lane;            // my word's first record
+    u32 w = i0 < n ? bits[i0 >> 5] : 0u;
+    if (i0 < n && n - i0 < 32) w &= (1u << (n - i0)) - 1u;
+    const u32 c = warp_sum((u32)__popc(w));
+    if (lane == 0) tile_cnt[tile] = c;
+}
+__global__ void __launch_bounds__(1024) k_unpack_scan(u32 *__restrict__ tile_cnt, u64 n_tiles, u32 *__restrict__ id_counter)
+{
+    __shared__ u32 s_warp[32];
+    __shared__ u32 s_run;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_run = *id_counter;
+    __syncthreads();
+    for (u64 t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const u64 t = t0 + tid;
+        const u32 v = t < n_tiles ? tile_cnt[t] : 0u;
+        u32 x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        u32 wbase = 0, all = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const u32 q = s_warp[k]; if (k < (int)wid) wbase += q; all += q; }
+        const u32 run = s_run;
+        if (t < n_tiles) tile_cnt[t] = run + wbase + x - v;      // ids handed out before this tile
+        __syncthreads();
+        if (tid == 0) s_run = run + all;
+        __syncthreads();
+    }
+    if (tid == 0) *id_counter = s_run;
+}
+__global__ void k_unpack_write(const u32 *__restrict__ bits, const unsigned short *__restrict__ ref16, u64 n, const u32 *__restrict__ tile_base,
+                               u32 *__restrict__ rid, u32 *__restrict__ ref)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 tile = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_tiles = (n + UNPACK_TILE - 1) / UNPACK_TILE;
+    if (tile >= n_tiles) return;
+    const u64 t0 = tile * UNPACK_TILE, i0 = t0 + 32ull * lane;
+    u32 w = i0 < n ? bits[i0 >> 5] : 0u;
+    if (i0 < n && n - i0 < 32) w &= (1u << (n - i0)) - 1u;
+    u32 incl = (u32)__popc(w);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += y; }
+    const u32 before = tile_base[tile] + incl - (u32)__popc(w);  // set bits before my word
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const u32 wj = __shfl_sync(FULL, w, j), bj = __shfl_sync(FULL, before, j);
+        const u64 i = t0 + 32ull * j + lane;
+        if (i < n) {
+            rid[i] = bj + (u32)__popc(wj & LANE_LE(lane)) - 1u;
+            ref[i] = ref16[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // helpers for the unsorted-input path and bin readout
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pack_values(const u32 *__restrict__ ref, const i32 *__restrict__ pos, u64 n, uint2 *__restrict__ out)

@@ -81,6 +81,9 @@ struct slimm_gpu_ctx {
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
     u32 **d_dest = nullptr; u32 **d_peer_recv = nullptr; u32 *d_n_recv = nullptr;   // d_n_recv[0]: items this rank receives, [1]: a receive buffer would overflow
     bool n_recv_on_device = false;          // the split was planned on the device (slimm_gpu_split_to_peers_device): n_recv lives there
+    // slimm_gpu_push_packed: staging of the wire format + the running read-id counter
+    u32 *d_pk_bits = nullptr; unsigned short *d_pk_ref16 = nullptr; u32 *d_pk_tiles = nullptr, *d_pk_counter = nullptr; u64 pk_cap = 0;
+    int push_kind = 0;                      // 0: nothing pushed yet, 1: slimm_gpu_push, 2: slimm_gpu_push_packed
     bool verify_pending = false;            // the optimistic checks of the coverage stage (ids non-decreasing, reference ids in range) have not been read back yet
     // fine slices: the histogram is accumulated in shared memory, 2^14 bins per CTA (k_fine_*)
     u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr, *d_fine_hot = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
@@ -332,6 +335,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
     if (ctx->fold_done) cudaEventDestroy(ctx->fold_done);
     cudaFree(ctx->d_cut_sorted); cudaFree(ctx->d_cut_prefix);
+    cudaFree(ctx->d_pk_bits); cudaFree(ctx->d_pk_ref16); cudaFree(ctx->d_pk_tiles); cudaFree(ctx->d_pk_counter);
     delete ctx;
     return SLIMM_GPU_OK;
 }
@@ -343,6 +347,7 @@ int slimm_gpu_reset(slimm_gpu_ctx *ctx, uint32_t bin_width, uint32_t avg_read_le
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->external) { ctx->d_rid = ctx->d_ref = nullptr; ctx->d_pos = nullptr; ctx->cap = 0; ctx->external = false; }
     ctx->n = 0; ctx->stage = ST_CREATED; ctx->use_sorted = false; ctx->have_global_hits = false; ctx->h_assign_ok = false; ctx->finished = false;
+    ctx->push_kind = 0; ctx->verify_pending = false;
     if (avg_read_length) ctx->avg = avg_read_length;
     if (bin_width && bin_width != ctx->w) { ctx->w = bin_width; return layout_bins(ctx); }
     return SLIMM_GPU_OK;
@@ -381,13 +386,52 @@ int slimm_gpu_push(slimm_gpu_ctx *ctx, const uint32_t *read_id, const uint32_t *
     if (ctx->stage != ST_CREATED) return fail(ctx, SLIMM_GPU_ESTATE, "push after coverage; call slimm_gpu_reset first");
     if (ctx->external) return fail(ctx, SLIMM_GPU_ESTATE, "push after push_device");
     if (ctx->n + n > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-256 records in one context");
+    if (ctx->push_kind == 2) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_push and slimm_gpu_push_packed cannot be mixed inside a sample");
     if (n == 0) return SLIMM_GPU_OK;
+    ctx->push_kind = 1;
     CU(cudaSetDevice(ctx->device));
     int rc = reserve(ctx, ctx->n + n);
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->d_rid + ctx->n, read_id, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaMemcpyAsync(ctx->d_ref + ctx->n, ref_id, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaMemcpyAsync(ctx->d_pos + ctx->n, begin_pos, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->n += n;
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_push_packed(slimm_gpu_ctx *ctx, const uint32_t *new_read_bits, const uint16_t *ref_id16, const int32_t *begin_pos, uint64_t n)
+{
+    if (!ctx || (n && (!new_read_bits || !ref_id16 || !begin_pos))) return SLIMM_GPU_EINVAL;
+    if (ctx->stage != ST_CREATED) return fail(ctx, SLIMM_GPU_ESTATE, "push after coverage; call slimm_gpu_reset first");
+    if (ctx->external) return fail(ctx, SLIMM_GPU_ESTATE, "push after push_device");
+    if (ctx->push_kind == 1) return fail(ctx, SLIMM_GPU_ESTATE, "slimm_gpu_push and slimm_gpu_push_packed cannot be mixed inside a sample");
+    if (ctx->G > 65536) return fail(ctx, SLIMM_GPU_EINVAL, "the packed wire format needs fewer than 65 537 contigs");
+    if (ctx->n + n > SLIMM_MAX_RECORDS) return fail(ctx, SLIMM_GPU_ERANGE, "more than 2^32-256 records in one context");
+    if (n == 0) return SLIMM_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->n + n);
+    if (rc) return rc;
+    if (ctx->pk_cap < n) {                    // the copy stream orders a refill behind the kernels that read the staging area
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        cudaFree(ctx->d_pk_bits); cudaFree(ctx->d_pk_ref16); cudaFree(ctx->d_pk_tiles);
+        ctx->d_pk_bits = nullptr; ctx->d_pk_ref16 = nullptr; ctx->d_pk_tiles = nullptr; ctx->pk_cap = 0;
+        CU(cudaMalloc(&ctx->d_pk_bits, (n + 31) / 32 * 4 + 4)); CU(cudaMalloc(&ctx->d_pk_ref16, n * 2 + 2));
+        CU(cudaMalloc(&ctx->d_pk_tiles, ((n + UNPACK_TILE - 1) / UNPACK_TILE + 1) * 4));
+        ctx->pk_cap = n;
+    }
+    if (!ctx->d_pk_counter) { CU(cudaMalloc(&ctx->d_pk_counter, 4)); }
+    if (ctx->push_kind == 0) CU(cudaMemsetAsync(ctx->d_pk_counter, 0, 4, ctx->copy_stream));   // a new sample: ids start at 0
+    ctx->push_kind = 2;
+    CU(cudaMemcpyAsync(ctx->d_pos + ctx->n, begin_pos, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->d_pk_ref16, ref_id16, n * 2, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->d_pk_bits, new_read_bits, (n + 31) / 32 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    const u64 n_tiles = (n + UNPACK_TILE - 1) / UNPACK_TILE;
+    const unsigned grid = (unsigned)((n_tiles * 32 + 255) / 256);
+    k_unpack_count<<<grid, 256, 0, ctx->copy_stream>>>(ctx->d_pk_bits, n, ctx->d_pk_tiles);
+    k_unpack_scan<<<1, 1024, 0, ctx->copy_stream>>>(ctx->d_pk_tiles, n_tiles, ctx->d_pk_counter);
+    k_unpack_write<<<grid, 256, 0, ctx->copy_stream>>>(ctx->d_pk_bits, ctx->d_pk_ref16, n, ctx->d_pk_tiles, ctx->d_rid + ctx->n, ctx->d_ref + ctx->n);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
     ctx->n += n;
     return SLIMM_GPU_OK;
 }

@@ -295,3 +295,40 @@ def test_hot_fine_slice():
         np.testing.assert_array_equal(gpu.fetch_bins(0, 0), res.cov[a:b])
         np.testing.assert_array_equal(gpu.fetch_bins(1, 0), res.uniq_cov[a:b])
         np.testing.assert_array_equal(gpu.ref_stats().reads_count, res.reads_count)
+
+
+def _pack(read_id, ref_id):
+    """The wire format of grouped input: bit i set when record i starts a read, 16-bit reference ids."""
+    n = read_id.size
+    new = np.ones(n, dtype=bool)
+    new[1:] = read_id[1:] != read_id[:-1]
+    bits = np.packbits(np.concatenate([new, np.zeros((-n) % 32, dtype=bool)]), bitorder="little").view(np.uint32)
+    return bits, ref_id.astype(np.uint16)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_push_packed_wire_format(mode):
+    """slimm_gpu_push_packed (one new-read bit + u16 reference id + position per record) in uneven batches gives what
+    slimm_gpu_push gives: the ids rebuilt on the device are the dense ids, continued across batches."""
+    contigs, rec, lineage = _synthetic(1000, 700_000, 321, multi_frac=0.3)
+    res = oracle.run(contigs.lengths, lineage, 500, 100, 0.9, rec.read_id, rec.ref_id, rec.begin_pos)
+    cuts = [0, 1, 33, 100_001, 100_001, 433_333, rec.read_id.size]          # one-record, empty and odd-sized batches
+    with api.SlimmGpu(contigs.lengths, lineage, 500, 100, flags=api.KEEP_UNIQ_COV2 | api.READ_RESULTS) as gpu:
+        for _ in range(2):                                                   # the id counter restarts with every sample
+            gpu.reset()
+            gpu.set_scatter_mode(mode)
+            for a, b in zip(cuts, cuts[1:]):
+                # a batch's own bit array starts at bit 0; a read may straddle two batches (its later records carry bit 0)
+                new = np.ones(b - a, dtype=bool)
+                new[1:] = rec.read_id[a + 1:b] != rec.read_id[a:b - 1]
+                if a and b > a:
+                    new[0] = rec.read_id[a] != rec.read_id[a - 1]
+                bits = np.packbits(np.concatenate([new, np.zeros((-(b - a)) % 32, dtype=bool)]), bitorder="little")
+                bits = np.concatenate([bits, np.zeros((-bits.size) % 4, dtype=np.uint8)]).view(np.uint32)
+                gpu.push_packed(bits, rec.ref_id[a:b].astype(np.uint16), rec.begin_pos[a:b])
+            gpu.run(0.9)
+            compare_with_oracle(gpu, res, lineage, check_bins=False)
+        with pytest.raises(api.SlimmGpuError):                               # the two ingest formats do not mix inside a sample
+            gpu.reset()
+            gpu.push(rec.read_id[:10], rec.ref_id[:10], rec.begin_pos[:10])
+            gpu.push_packed(*_pack(rec.read_id[10:20], rec.ref_id[10:20]), rec.begin_pos[10:20])
