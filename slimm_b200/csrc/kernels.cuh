@@ -1554,6 +1554,8 @@ struct Lin16 { uint4 v; };
 struct Lin32 { uint4 a, b; };
 __device__ __forceinline__ void lin_load(const uint4 *__restrict__ t, u32 g, Lin16 &o) { o.v = __ldg(t + g); }
 __device__ __forceinline__ void lin_load(const uint4 *__restrict__ t, u32 g, Lin32 &o) { o.a = __ldg(t + 2 * (u64)g); o.b = __ldg(t + 2 * (u64)g + 1); }
+__device__ __forceinline__ bool lin_row_valid(const Lin16 &o) { return (o.v.w >> 31) != 0; }    // k_lin_valid's bit
+__device__ __forceinline__ bool lin_row_valid(const Lin32 &) { return false; }                  // (never used: VROW is a Lin16 matter)
 __device__ __forceinline__ void lin_zero(Lin16 &o) { o.v = make_uint4(0, 0, 0, 0); }
 __device__ __forceinline__ void lin_zero(Lin32 &o) { o.a = make_uint4(0, 0, 0, 0); o.b = o.a; }
 // acc |= x ^ y, slot by slot
@@ -1581,13 +1583,29 @@ __device__ __forceinline__ u32 lin_neq(const Lin32 &acc)
            ((u32)(acc.b.x != 0) << 4) | ((u32)(acc.b.y != 0) << 5) | ((u32)(acc.b.z != 0) << 6) | ((u32)(acc.b.w != 0) << 7);
 }
 
+// the per-sample copy of the 16-bit lineage rows with the valid bit of the reference folded into bit 15 of slot 7 (the dense
+// index of the top level never needs it): one 16-byte gather per compact word instead of a row and a bit from two tables
+__global__ void k_lin_valid(const uint4 *__restrict__ lin16, const u32 *__restrict__ vb, u32 G, uint4 *__restrict__ out)
+{
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    uint4 r = lin16[g];
+    r.w = (r.w & 0x7FFFFFFFu) | (is_valid(vb, g) ? 0x80000000u : 0u);
+    out[g] = r;
+}
+
+#define ASG_STAGE 512u              // compact words of a warp's 32 reads staged in shared memory (more: read in place)
+
 // EXTRA: uniq_cov2 bins / per-read results are wanted (they need the record index of every compact word)
-template <class Rec, class Lin, bool EXTRA>
+// VROW:  lin_tab is the per-sample table of k_lin_valid (Lin16 only): the row carries the valid bit
+template <class Rec, class Lin, bool EXTRA, bool VROW>
 __global__ void __launch_bounds__(256, EXTRA ? 4 : ASSIGN_READS_OCC)
-k_assign_reads(Rec rec, u32 n, AssignParams P, const u32 *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
+k_assign_reads(const __grid_constant__ Rec rec, u32 n, const __grid_constant__ AssignParams P, const u32 *__restrict__ rs_all, const uint4 *__restrict__ lin_tab)
 {
     __shared__ u32 s_key[LCA_CACHE], s_val[LCA_CACHE];
+    __shared__ u32 s_stage[8][ASG_STAGE];
     const u32 lane = threadIdx.x & 31;
+    u32 *const st = s_stage[threadIdx.x >> 5];
     for (u32 k = threadIdx.x; k < LCA_CACHE; k += blockDim.x) { s_key[k] = LCA_EMPTY; s_val[k] = 0; }
     __syncthreads();
     const u32 n_chunks = n / CHUNK + (n % CHUNK != 0);
@@ -1599,21 +1617,33 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const u32 *__restrict__ rs_all, c
         const u32 *rs = rs_all + (u64)c * RS_SLOT;
         for (u32 k0 = 0; k0 < n_rs; k0 += 32) {
             const u32 k = k0 + lane;
-            if (k >= n_rs) continue;
-            const u32 entry = __ldg(rs + k);                       // start | words << 16 (at most 32 words)
+            const bool active = k < n_rs;
+            const u32 entry = active ? __ldg(rs + k) : 0u;         // start | words << 16 (at most 32 words)
             const u32 start = entry & 0xFFFFu, end = start + (entry >> 16);
+            // the words of the warp's 32 reads lie next to each other (gaps where repeat hits were): one coalesced copy into shared
+            // memory, then every lane walks its own read there instead of 32 lanes reading 32 places of global memory
+            const u32 lo = __shfl_sync(FULL, start, 0), hi = __shfl_sync(FULL, end, (int)min(31u, n_rs - k0 - 1u));
+            const bool staged = hi - lo <= ASG_STAGE;              // warp-uniform
+            __syncwarp();
+            if (staged) for (u32 w = lane; w < hi - lo; w += 32) st[w] = __ldcs(cw + lo + w);
+            __syncwarp();
+            auto word = [&](u32 j) { return (staged ? st[j - lo] : __ldg(cw + j)) & ~CW_HEAD; };
+            if (!active) continue;
             u32 g0 = 0, j0 = start, ns = 0, gmax = 0, vmask = 0;  // vmask: which of the read's (at most 32) words survive
             Lin l0, acc;
             lin_zero(l0); lin_zero(acc);
             for (u32 j = start; j < end; j += 4) {
                 u32 g[4]; bool v[4]; Lin l[4];
 #pragma unroll
-                for (int d = 0; d < 4; ++d) g[d] = j + d < end ? (__ldg(cw + j + d) & ~CW_HEAD) : 0xFFFFFFFFu;
+                for (int d = 0; d < 4; ++d) g[d] = j + d < end ? word(j + d) : 0xFFFFFFFFu;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {                      // the valid bit and the lineage row travel together
                     v[d] = false;
                     lin_zero(l[d]);
-                    if (g[d] != 0xFFFFFFFFu) { v[d] = is_valid(P.vb, g[d]); lin_load(lin_tab, g[d], l[d]); }
+                    if (g[d] != 0xFFFFFFFFu) {
+                        lin_load(lin_tab, g[d], l[d]);
+                        v[d] = VROW ? lin_row_valid(l[d]) : is_valid(P.vb, g[d]);
+                    }
                 }
 #pragma unroll
                 for (int d = 0; d < 4; ++d)
@@ -1648,7 +1678,7 @@ k_assign_reads(Rec rec, u32 n, AssignParams P, const u32 *__restrict__ rs_all, c
                         if (vmask) {
                             const u32 b = (u32)__ffs(vmask) - 1u;
                             vmask &= vmask - 1u;
-                            mk[d] = mk_base + (u64)(__ldg(cw + start + b) & ~CW_HEAD) * mk_stride;
+                            mk[d] = mk_base + (u64)word(start + b) * mk_stride;
                         }
                     }
 #pragma unroll

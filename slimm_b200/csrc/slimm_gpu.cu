@@ -48,6 +48,7 @@ struct slimm_gpu_ctx {
     u32 *d_cw = nullptr, *d_cw_idx = nullptr, *d_lr = nullptr; uint2 *d_chunk_cnt = nullptr; u64 cw_chunks = 0;   // compact stream for k_assign
     u32 *d_rs = nullptr;                    // per chunk: start | words << 16 of every multi-target read inside the chunk's compact words
     uint4 *d_lin16 = nullptr;               // lineages as 8 x 16-bit per-level dense taxon indices (fewer than 65536 references)
+    uint4 *d_lin16v = nullptr;              // per sample: the same rows with the valid bit folded in (k_lin_valid); null: top level too wide
     BinDiv wdiv{0, 0, 0};
     int scatter_mode = -1;                  // -1 auto, 0 direct, 1 bucketed
     int cutoff_mode = -1;                   // -1 auto (cluster/DSMEM sort when it fits), 1 global-memory sort
@@ -285,6 +286,7 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
             u32 k = 0;
             for (auto &kv : idx) kv.second = k++;
             for (u32 g = 0; g < G; ++g) l16[(size_t)g * 8 + l] = (unsigned short)idx[ctx->h_lin[(size_t)g * 8 + l]];
+            if (l == 7 && k <= 32768) CU(cudaMalloc(&ctx->d_lin16v, (size_t)G * 16));   // bit 15 of slot 7 is free for the valid flag
         }
         CU(cudaMalloc(&ctx->d_lin16, (size_t)G * 16));
         CU(cudaMemcpy(ctx->d_lin16, l16.data(), (size_t)G * 16, cudaMemcpyHostToDevice));
@@ -320,7 +322,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
-    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_dest); cudaFree(ctx->d_peer_recv); cudaFree(ctx->d_n_recv);
+    cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_lin16v); cudaFree(ctx->d_dest); cudaFree(ctx->d_peer_recv); cudaFree(ctx->d_n_recv);
     cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref); cudaFree(ctx->d_fine_hot);
     for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
     cudaFree(ctx->d_recv);
@@ -1081,19 +1083,22 @@ int slimm_gpu_assign(slimm_gpu_ctx *ctx)
         const int rgrid = (int)std::max<u64>(1, std::min<u64>((n_chunks + 7) / 8, (u64)ctx->sm_count * asg_ctas));
         const uint4 *lin32 = (const uint4 *)ctx->d_lin;
         const bool extra = ctx->d_cw_idx != nullptr || P.res_kind != nullptr;
+        const bool vrow = ctx->d_lin16v != nullptr;
+        if (vrow) { k_lin_valid<<<(G + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lin16, ctx->d_valid_bits, G, ctx->d_lin16v); ctx->launches++; }
+        auto launch = [&](auto rec) {
+            using R = decltype(rec);
+            if (vrow && extra) k_assign_reads<R, Lin16, true, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16v);
+            else if (vrow) k_assign_reads<R, Lin16, false, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16v);
+            else if (extra && ctx->d_lin16) k_assign_reads<R, Lin16, true, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else if (extra) k_assign_reads<R, Lin32, true, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            else if (ctx->d_lin16) k_assign_reads<R, Lin16, false, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
+            else k_assign_reads<R, Lin32, false, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+        };
         if (ctx->use_sorted) {
-            const RecPacked rec{ctx->d_rid_sorted, ctx->d_rp_sorted};
-            if (extra && ctx->d_lin16) k_assign_reads<RecPacked, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else if (extra) k_assign_reads<RecPacked, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
-            else if (ctx->d_lin16) k_assign_reads<RecPacked, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else k_assign_reads<RecPacked, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            launch(RecPacked{ctx->d_rid_sorted, ctx->d_rp_sorted});
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, (const u32 *)ctx->d_rp_sorted, 2, ctx->d_valid_bits, n);
         } else {
-            const RecSoA rec{ctx->d_rid, ctx->d_ref, ctx->d_pos};
-            if (extra && ctx->d_lin16) k_assign_reads<RecSoA, Lin16, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else if (extra) k_assign_reads<RecSoA, Lin32, true><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
-            else if (ctx->d_lin16) k_assign_reads<RecSoA, Lin16, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, ctx->d_lin16);
-            else k_assign_reads<RecSoA, Lin32, false><<<rgrid, 256, 0, ctx->stream>>>(rec, n, P, ctx->d_rs, lin32);
+            launch(RecSoA{ctx->d_rid, ctx->d_ref, ctx->d_pos});
             if (P.res_kind) k_read_results_unique<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_kind, ctx->d_val, ctx->d_ref, 1, ctx->d_valid_bits, n);
         }
         ctx->launches += 1 + (P.res_kind ? 1 : 0);
