@@ -168,6 +168,16 @@ int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts /* [
  * [n_ranks][n_slices]); no host copy of the counts, no synchronisation - coverage, the collectives and the split queue up on the
  * stream.  A receive buffer that would overflow is reported by slimm_gpu_get_summary (SLIMM_GPU_ERANGE). */
 int slimm_gpu_slice_counts_device(slimm_gpu_ctx *ctx, void **d_counts, uint32_t *n_slices);
+
+/* ---- several GPUs driven by ONE host process (the C++ front end: `slimm --gpus N`) -----------------------------------
+ * ctxs[0..n): contexts on n different devices, created from the same configuration, slimm_gpu_set_shard(r, n) done, each fed
+ * the records of ITS reads (all records of a read in one context, read ids non-decreasing per context).  Runs the whole path:
+ * coverage everywhere, the items to the owners of their histogram slices (n x n peer copies, each source's share of an owner
+ * is one contiguous block), accumulate, the per-reference statistics summed, filter and assign everywhere, the assign blocks
+ * summed.  Afterwards every context answers slimm_gpu_get_summary / get_ref_stats / profile with the global results.  No NCCL,
+ * no second process: cudaMemcpyPeerAsync and host-side sums of 16 bytes per reference and the assign block.
+ * global_hits: kept records over all contexts.  Replaces, like slimm_gpu_run, reference src/slimm.hpp:449,464,485. */
+int slimm_gpu_run_sharded_local(slimm_gpu_ctx **ctxs, uint32_t n, float cov_cut_off, uint32_t min_reads, uint64_t global_hits);
 int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_counts);
 int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx);
 /* back to the all-to-all exchange (e.g. when another rank could not map the buffers) */

@@ -423,7 +423,8 @@ public:
     }
 
     // Decodes the whole file.  sink(batch) is called on the calling thread with every filled batch (and the last,
-    // partial one); it returns the batch to fill next (double buffering is the sink's business).
+    // partial one); it returns the batch to fill next (double buffering is the sink's business) with n = the records it
+    // already holds (0, or the tail of a read the sink moved over so that a read never straddles two batches).
     // assume_grouped: dense ids by counting runs of equal names, verified in parallel (RunHeadSet).  When the file
     // turns out not to be grouped by read the call stops early with st.not_grouped set (and returns false with an
     // empty err): the caller discards what the sink received and calls decode again with assume_grouped = false.
@@ -503,7 +504,7 @@ public:
                         if (next_id >= 0xFFFFFFFEull) { err = "more than 2^32-2 distinct reads"; ok = false; break; }
                         ++next_id;
                     }
-                    if (batch.n == batch.cap) { batch = sink(batch); batch.n = 0; }
+                    if (batch.n == batch.cap) batch = sink(batch);   // the sink hands back the batch to fill next (n = records it already holds)
                     batch.read_id[batch.n] = (uint32_t)(next_id - 1); batch.ref_id[batch.n] = ch.ref[i]; batch.begin_pos[batch.n] = ch.pos[i];
                     ++batch.n;
                 }
@@ -525,7 +526,7 @@ public:
                     id = table.lookup_or_insert(ch.hash[i], key, len);
                     prev_key.assign(key, len); prev_hash = ch.hash[i]; prev_id = id; have_prev = true;
                 }
-                if (batch.n == batch.cap) { batch = sink(batch); batch.n = 0; }
+                if (batch.n == batch.cap) batch = sink(batch);   // the sink hands back the batch to fill next (n = records it already holds)
                 batch.read_id[batch.n] = id; batch.ref_id[batch.n] = ch.ref[i]; batch.begin_pos[batch.n] = ch.pos[i];
                 ++batch.n;
             }

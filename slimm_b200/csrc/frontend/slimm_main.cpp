@@ -14,6 +14,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -44,6 +45,7 @@ struct Options {
     std::string dump_records;        // --dump-records FILE: decode only, write the SoA (test hook, needs no GPU)
     bool exact_ids = false;          // --exact-ids: always assign read ids through the name table (skip the grouped-input fast path)
     int threads = 0, device = 0;
+    int gpus = 1;                    // --gpus N: reads sharded over N devices of this host (slimm_gpu_run_sharded_local)
 };
 
 struct Timer {
@@ -83,6 +85,10 @@ static std::vector<std::string> get_bam_files_in_directory(const std::string &di
         if (full.find(".sam") == full.find_last_of(".") || full.find(".bam") == full.find_last_of(".")) out.push_back(full);
     }
     closedir(dir);
+    // The reference takes the files in readdir() order, which no two file systems agree on - and its -w / -mr defaults stick from the
+    // first file on.  Sorted by name the run is reproducible, and samples mapped against the same references (same @SQ lines) sit
+    // next to each other more often than not, so the GPU context is reused
+    std::sort(out.begin(), out.end());
     return out;
 }
 
@@ -114,7 +120,8 @@ static void print_help()
                  "    -co, --coverage-output        Output raw coverage statstics\n"
                  "    -v, --verbose                 Enable verbose output.\n"
                  "    --threads INT                 host decode threads (default: all cores); --device INT  CUDA device (default 0)\n"
-                 "    --exact-ids                   always assign read ids through the read-name table (skip the grouped-input fast path)\n";
+                 "    --exact-ids                   always assign read ids through the read-name table (skip the grouped-input fast path)\n"
+                 "    --gpus INT                    shard the reads over INT GPUs of this host, starting at --device (profile-only runs)\n";
 }
 
 static bool parse_number(const std::string &s, double &v)
@@ -172,6 +179,7 @@ static int parse_command_line(int argc, char **argv, Options &o)
             else if (a == "-v" || a == "--verbose") o.verbose = true;
             else if (a == "--threads") { if (!value(s)) return 1; o.threads = atoi(s.c_str()); }
             else if (a == "--device") { if (!value(s)) return 1; o.device = atoi(s.c_str()); }
+            else if (a == "--gpus") { if (!value(s)) return 1; o.gpus = std::max(1, atoi(s.c_str())); }
             else if (a == "--dump-records") { if (!value(o.dump_records)) return 1; }
             else if (a == "--exact-ids") o.exact_ids = true;
             else { std::cerr << "slimm: illegal option -- " << a << "\n"; return 1; }
@@ -225,6 +233,23 @@ static std::string lineage_string(uint32_t rank, const uint32_t *lin, const Slim
 struct FileState {
     uint32_t hits_count = 0;
 };
+static double g_db_seconds = 0;      // loading the .sldb (reported under -v)
+
+// The GPU side of a run: one context per device (--gpus), kept across the files of a directory as long as the @SQ lines (and
+// the outputs asked for) stay the same - the bin layout, the lineage tables and the device buffers are reused and only
+// slimm_gpu_reset runs between samples (reference slimm::reset(), src/slimm.hpp:167-188, does the same for its members).
+struct GpuSet {
+    std::vector<slimm_gpu_ctx *> ctx;
+    std::vector<std::string> names;
+    std::vector<uint32_t> lengths;
+    uint32_t flags = 0;
+    int device = -1;
+    bool matches(const AlignmentHeader &hd, uint32_t f, int dev, int n) const
+    {
+        return !ctx.empty() && (int)ctx.size() == n && flags == f && device == dev && names == hd.names && lengths == hd.lengths;
+    }
+    void destroy() { for (slimm_gpu_ctx *c : ctx) slimm_gpu_destroy(c); ctx.clear(); }
+};
 
 static bool dump_records_file(const Options &opt, AlignmentDecoder &dec, uint32_t avg, int threads)
 {
@@ -244,6 +269,7 @@ static bool dump_records_file(const Options &opt, AlignmentDecoder &dec, uint32_
         ok = dec.decode(threads, batch, [&](RecordBatch b) {
             rid.insert(rid.end(), b.read_id, b.read_id + b.n); ref.insert(ref.end(), b.ref_id, b.ref_id + b.n);
             pos.insert(pos.end(), b.begin_pos, b.begin_pos + b.n);
+            b.n = 0;
             return b;
         }, st, err, attempt == 0);
         if (ok || !st.not_grouped) break;
@@ -379,7 +405,7 @@ static void write_coverage(const Options &opt, const std::string &input, slimm_g
 }
 
 // slimm::get_profiles (reference src/slimm.hpp:395-496) for one file; returns false when the file could not be read
-static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &input, uint32_t index, uint32_t n_files, FileState &fs)
+static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &input, uint32_t index, uint32_t n_files, FileState &fs, GpuSet &gs)
 {
     Timer watch;
     std::cerr << "\nReading " << index + 1 << " of " << n_files << " files ... (" << get_file_name(input) << ")\n"
@@ -404,29 +430,56 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
         auto it = db.ac__taxid.find(accession[g]);
         if (it != db.ac__taxid.end()) { taxa_id[g] = it->second[0]; memcpy(&lineage[(size_t)g * 8], it->second.data(), 32); }
     }
-    slimm_gpu_config cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.n_refs = G; cfg.ref_len = hd.lengths.data(); cfg.lineage = lineage.data(); cfg.bin_width = opt.bin_width;
-    cfg.avg_read_length = avg_read_length; cfg.device = opt.device;
-    cfg.flags = (opt.raw_output || opt.coverage_output) ? SLIMM_GPU_KEEP_UNIQ_COV2 : SLIMM_GPU_SKIP_BINS;   // profile-only runs never read the bins back
-    slimm_gpu_ctx *ctx = nullptr;
-    int rc = slimm_gpu_create(&cfg, &ctx);
-    if (rc != SLIMM_GPU_OK) {
-        std::cerr << "\nslimm: cannot set up the GPU hot path: " << slimm_gpu_strerror(rc);
-        if (ctx && *slimm_gpu_last_error(ctx)) std::cerr << " (" << slimm_gpu_last_error(ctx) << ")";
-        std::cerr << "\n";
-        if (ctx) slimm_gpu_destroy(ctx);
+    const uint32_t flags = (opt.raw_output || opt.coverage_output) ? SLIMM_GPU_KEEP_UNIQ_COV2 : SLIMM_GPU_SKIP_BINS;   // profile-only runs never read the bins back
+    const int n_gpus = opt.gpus;
+    if (n_gpus > 1 && (opt.raw_output || opt.coverage_output)) {
+        std::cerr << "\nslimm: --gpus works for profile-only runs (the bins of -ro / -co stay on the GPU that owns their histogram slice)\n";
         exit(1);
     }
+    Timer ct;
+    const bool reuse = gs.matches(hd, flags, opt.device, n_gpus);
+    if (!reuse) {
+        gs.destroy();
+        slimm_gpu_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.n_refs = G; cfg.ref_len = hd.lengths.data(); cfg.lineage = lineage.data(); cfg.bin_width = opt.bin_width;
+        cfg.avg_read_length = avg_read_length; cfg.flags = flags;
+        for (int r = 0; r < n_gpus; ++r) {
+            cfg.device = opt.device + r;
+            slimm_gpu_ctx *c = nullptr;
+            const int rc = slimm_gpu_create(&cfg, &c);
+            if (rc != SLIMM_GPU_OK) {
+                std::cerr << "\nslimm: cannot set up the GPU hot path on device " << cfg.device << ": " << slimm_gpu_strerror(rc);
+                if (c && *slimm_gpu_last_error(c)) std::cerr << " (" << slimm_gpu_last_error(c) << ")";
+                std::cerr << "\n";
+                if (c) slimm_gpu_destroy(c);
+                gs.destroy();
+                exit(1);
+            }
+            gs.ctx.push_back(c);
+        }
+        gs.names = hd.names; gs.lengths = hd.lengths; gs.flags = flags; gs.device = opt.device;
+    }
+    slimm_gpu_ctx *ctx = gs.ctx[0];                               // after the run every context answers with the global results
     bool ok = true;
+    double ctx_sec = 0, gsec = 0, dsec = 0;
     try {
-        std::vector<uint32_t> t_id; std::vector<uint8_t> t_rank, t_named;
-        for (const auto &kv : db.taxid__name) { t_id.push_back(kv.first); t_rank.push_back(kv.second.first); t_named.push_back(!kv.second.second.empty()); }
-        check(slimm_gpu_set_taxa(ctx, t_id.size(), t_id.data(), t_rank.data(), t_named.data()), ctx, "slimm_gpu_set_taxa");
+        for (int r = 0; r < n_gpus; ++r) {
+            if (reuse) check(slimm_gpu_reset(gs.ctx[r], opt.bin_width, avg_read_length), gs.ctx[r], "slimm_gpu_reset");
+            if (n_gpus > 1) check(slimm_gpu_set_shard(gs.ctx[r], (uint32_t)r, (uint32_t)n_gpus), gs.ctx[r], "slimm_gpu_set_shard");
+        }
+        if (!reuse) {
+            std::vector<uint32_t> t_id; std::vector<uint8_t> t_rank, t_named;
+            for (const auto &kv : db.taxid__name) { t_id.push_back(kv.first); t_rank.push_back(kv.second.first); t_named.push_back(!kv.second.second.empty()); }
+            for (slimm_gpu_ctx *c : gs.ctx) check(slimm_gpu_set_taxa(c, t_id.size(), t_id.data(), t_rank.data(), t_named.data()), c, "slimm_gpu_set_taxa");
+        }
+        ctx_sec = ct.elapsed();
         std::cerr << "[" << watch.lap() << " secs]" << std::endl;
 
         std::cerr << "Analysing alignments, reads and references ....... ";
-        // decode threads fill pinned struct-of-arrays batches; each full batch is uploaded asynchronously while the next fills
+        // decode threads fill pinned struct-of-arrays batches; each full batch is uploaded asynchronously while the next fills.
+        // Several GPUs: batch k goes to device k mod N, cut at the last read boundary (the tail moves into the next batch), so
+        // every read lives on one device and every device sees non-decreasing read ids
         const size_t cap = 1u << 22;
         const int NB = 3;
         void *pin[NB] = {nullptr, nullptr, nullptr};
@@ -437,46 +490,64 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
             batches[b].begin_pos = (int32_t *)(batches[b].ref_id + cap); batches[b].cap = cap; batches[b].n = 0;
         }
         int cur = 0;
-        uint64_t pushed = 0;
+        uint64_t pushed = 0, turn = 0;
         DecodeStats st;
         Timer dt;
         bool dec_ok = false;
+        auto sync_all = [&] { for (slimm_gpu_ctx *c : gs.ctx) check(slimm_gpu_sync_uploads(c), c, "slimm_gpu_sync_uploads"); };
         // Mapper output is grouped by read: ids by counting runs, checked in parallel by the parse workers.  If a read name
         // comes back after its run has ended (coordinate-sorted input), what was pushed is dropped and the file is decoded
         // again through the exact name table.
         for (int attempt = (opt.exact_ids || threads < 3) ? 1 : 0; attempt < 2; ++attempt) {
-            cur = 0; pushed = 0;
+            cur = 0; pushed = 0; turn = 0;
             batches[0].n = 0;
             dec_ok = dec.decode(threads, batches[0], [&](RecordBatch b) {
-                check(slimm_gpu_push(ctx, b.read_id, b.ref_id, b.begin_pos, b.n), ctx, "slimm_gpu_push");
-                pushed += b.n;
-                cur = (cur + 1) % NB;
-                if (pushed >= (uint64_t)(NB - 1) * cap) check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");   // the buffer about to be refilled is free again
+                size_t cut = b.n;                                  // records of this batch that go out now
+                if (n_gpus > 1 && b.n == b.cap) {                  // a full batch (the last one never is): keep the last read together
+                    while (cut > 0 && b.read_id[cut - 1] == b.read_id[b.n - 1]) --cut;
+                    if (cut == 0) cut = b.n;                       // one read fills the whole batch: it stays on this device, no turn taken
+                }
+                slimm_gpu_ctx *to = gs.ctx[turn % (uint64_t)n_gpus];
+                check(slimm_gpu_push(to, b.read_id, b.ref_id, b.begin_pos, cut), to, "slimm_gpu_push");
+                if (!(n_gpus > 1 && cut == b.n && b.n == b.cap)) ++turn;   // (a batch that is one single read keeps the turn: its next records follow it)
+                pushed += cut;
+                const int nxt = (cur + 1) % NB;
+                if (pushed >= (uint64_t)(NB - 1) * cap) sync_all();   // the buffer about to be refilled is free again
+                const size_t tail = b.n - cut;
+                if (tail) {
+                    memcpy(batches[nxt].read_id, b.read_id + cut, tail * 4); memcpy(batches[nxt].ref_id, b.ref_id + cut, tail * 4);
+                    memcpy(batches[nxt].begin_pos, b.begin_pos + cut, tail * 4);
+                }
+                batches[nxt].n = tail;
+                cur = nxt;
                 return batches[cur];
             }, st, err, attempt == 0);
             if (dec_ok || !st.not_grouped) break;
-            check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");
-            check(slimm_gpu_reset(ctx, 0, 0), ctx, "slimm_gpu_reset");
+            sync_all();
+            for (slimm_gpu_ctx *c : gs.ctx) check(slimm_gpu_reset(c, 0, 0), c, "slimm_gpu_reset");
+            for (int r = 0; r < n_gpus && n_gpus > 1; ++r) check(slimm_gpu_set_shard(gs.ctx[r], (uint32_t)r, (uint32_t)n_gpus), gs.ctx[r], "slimm_gpu_set_shard");
             if (opt.verbose) std::cerr << "\n  (input is not grouped by read: decoding again with the exact read-name table) ";
         }
         if (!dec_ok) throw GpuError{SLIMM_GPU_EINVAL, input + ": " + err};
-        check(slimm_gpu_sync_uploads(ctx), ctx, "slimm_gpu_sync_uploads");
-        const double dsec = dt.elapsed();
+        sync_all();
+        dsec = dt.elapsed();
         for (int b = 0; b < NB; ++b) slimm_gpu_host_free(pin[b]);
         fs.hits_count = (uint32_t)st.records_kept;
         if (st.records_kept == 0) {
             std::cerr << "[" << watch.lap() << " secs]" << std::endl;
             std::cerr << "[WARNING] No mapped reads found in BAM file!" << std::endl;
-            slimm_gpu_destroy(ctx);
             return true;
         }
         Timer gt;
-        check(slimm_gpu_coverage(ctx), ctx, "slimm_gpu_coverage");
-        check(slimm_gpu_filter(ctx, opt.cov_cut_off, opt.min_reads), ctx, "slimm_gpu_filter");
-        check(slimm_gpu_assign(ctx), ctx, "slimm_gpu_assign");
+        if (n_gpus > 1) check(slimm_gpu_run_sharded_local(gs.ctx.data(), (uint32_t)n_gpus, opt.cov_cut_off, opt.min_reads, st.records_kept), ctx, "slimm_gpu_run_sharded_local");
+        else {
+            check(slimm_gpu_coverage(ctx), ctx, "slimm_gpu_coverage");
+            check(slimm_gpu_filter(ctx, opt.cov_cut_off, opt.min_reads), ctx, "slimm_gpu_filter");
+            check(slimm_gpu_assign(ctx), ctx, "slimm_gpu_assign");
+        }
         slimm_gpu_summary sm;
         check(slimm_gpu_get_summary(ctx, &sm), ctx, "slimm_gpu_get_summary");
-        const double gsec = gt.elapsed();
+        gsec = gt.elapsed();
         std::cerr << "[" << watch.lap() << " secs]" << std::endl;
         if (opt.min_reads == 0) opt.min_reads = sm.min_reads;     // reference src/slimm.hpp:458-459 (persists across files)
         if (opt.verbose) {
@@ -493,6 +564,8 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
             std::cerr << "  uniq bins coverage cut-off = " << sm.uniq_coverage_cut_off << " (" << opt.cov_cut_off << " quantile)\n\n";
             std::cerr << "  decode: " << st.records_in_file << " records, " << st.reads << " reads in " << dsec << " s ("
                       << st.records_in_file / dsec / 1e6 << " M records/s, " << threads << " host threads); GPU stages: " << gsec * 1e3 << " ms\n";
+            std::cerr << "  phases: database " << g_db_seconds << " s (once), GPU context + tables " << ctx_sec << " s" << (reuse ? " (context reused)" : "")
+                      << ", decode + upload " << dsec << " s, GPU stages " << gsec << " s on " << n_gpus << " GPU(s)\n";
         }
         std::cerr << "Filtering unlikely sequences ..................... ";
         std::cerr << "[" << watch.lap() << " secs]" << std::endl;
@@ -525,8 +598,7 @@ static bool get_profiles(Options &opt, const SlimmDb &db, const std::string &inp
         std::cerr << "\nslimm: " << e.what << "\n";
         ok = false;
     }
-    slimm_gpu_destroy(ctx);
-    if (!ok) exit(1);
+    if (!ok) { gs.destroy(); exit(1); }
     return true;
 }
 
@@ -547,12 +619,15 @@ int main(int argc, char **argv)
     SlimmDb db;
     std::string err;
     if (opt.dump_records.empty() && !load_sldb(opt.database_path, db, err)) { std::cerr << "slimm: " << err << "\n"; return 1; }
+    g_db_seconds = watch.elapsed();
     uint32_t total_hits = 0;
+    GpuSet gs;
     for (uint32_t n = 0; n < inputs.size(); ++n) {
         FileState fs;
-        get_profiles(opt, db, inputs[n], n, (uint32_t)inputs.size(), fs);
+        get_profiles(opt, db, inputs[n], n, (uint32_t)inputs.size(), fs, gs);
         total_hits += fs.hits_count;
     }
+    gs.destroy();
     std::cerr << "\n*****************************************************************\n";
     std::cerr << total_hits << " SAM/BAM alignment records are proccessed.\n";
     std::cerr << "Taxonomic profiles are written to: \n   " << get_directory(opt.output_prefix) << "\n";

@@ -997,6 +997,84 @@ int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_co
     return SLIMM_GPU_OK;
 }
 
+// element-wise sum over the contexts of a device buffer (u32 words), through the host: small buffers only
+static int sum_over_contexts(slimm_gpu_ctx **ctxs, u32 n, u32 *(*get)(slimm_gpu_ctx *), u64 words)
+{
+    std::vector<u32> acc(words, 0), one(words);
+    for (u32 r = 0; r < n; ++r) {
+        slimm_gpu_ctx *ctx = ctxs[r];
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemcpyAsync(one.data(), get(ctx), words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (u64 i = 0; i < words; ++i) acc[i] += one[i];
+    }
+    for (u32 r = 0; r < n; ++r) {
+        slimm_gpu_ctx *ctx = ctxs[r];
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemcpyAsync(get(ctx), acc.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return SLIMM_GPU_OK;
+}
+
+int slimm_gpu_run_sharded_local(slimm_gpu_ctx **ctxs, uint32_t n, float cov_cut_off, uint32_t min_reads, uint64_t global_hits)
+{
+    if (!ctxs || n == 0) return SLIMM_GPU_EINVAL;
+    for (u32 r = 0; r < n; ++r)
+        if (!ctxs[r] || ctxs[r]->shard_n != n || ctxs[r]->shard_rank != r || ctxs[r]->G != ctxs[0]->G || ctxs[r]->Bp != ctxs[0]->Bp)
+            return fail(ctxs[r], SLIMM_GPU_ESTATE, "run_sharded_local: every context needs slimm_gpu_set_shard(r, n) and the same contigs");
+    if (n == 1) return slimm_gpu_run(ctxs[0], cov_cut_off, min_reads);
+    int rc;
+    for (u32 r = 0; r < n; ++r) {                                  // coverage on every device, back to back (asynchronous)
+        ctxs[r]->p2p = false;
+        if ((rc = slimm_gpu_coverage(ctxs[r]))) return rc;
+    }
+    const u32 ns = n_slices_of(ctxs[0]);
+    std::vector<u32> counts((size_t)n * ns);
+    for (u32 r = 0; r < n; ++r) {
+        u32 got = 0;
+        if ((rc = slimm_gpu_get_slice_counts(ctxs[r], counts.data() + (size_t)r * ns, ns, &got))) return rc;
+    }
+    // owner q receives, source by source, the block of each source's slice-grouped items that holds q's slices
+    for (u32 q = 0; q < n; ++q) {
+        slimm_gpu_ctx *ctx = ctxs[q];
+        u32 lo, hi;
+        owned_slices(ctx, q, &lo, &hi);
+        u64 total = 0;
+        for (u32 src = 0; src < n; ++src) for (u32 s = lo; s < hi; ++s) total += counts[(size_t)src * ns + s];
+        CU(cudaSetDevice(ctx->device));
+        if (ctx->recv_cap < total) {
+            cudaFree(ctx->d_recv); ctx->d_recv = nullptr; ctx->recv_cap = 0;
+            CU(cudaMalloc(&ctx->d_recv, std::max<u64>(total, 1) * 4));
+            ctx->recv_cap = total;
+        }
+        u64 off = 0;
+        for (u32 src = 0; src < n; ++src) {
+            u64 before = 0, mine = 0;
+            for (u32 s = 0; s < lo; ++s) before += counts[(size_t)src * ns + s];
+            for (u32 s = lo; s < hi; ++s) mine += counts[(size_t)src * ns + s];
+            if (mine) CU(cudaMemcpyPeerAsync(ctx->d_recv + off, ctx->device, ctxs[src]->d_grouped + before, ctxs[src]->device, mine * 4, ctx->stream));
+            off += mine;
+        }
+        ctx->n_recv = total;
+    }
+    for (u32 q = 0; q < n; ++q) {                                  // the copies read every source's buffer: all of them done before anybody goes on
+        slimm_gpu_ctx *ctx = ctxs[q];
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    for (u32 q = 0; q < n; ++q)
+        if ((rc = slimm_gpu_accumulate_items(ctxs[q], ctxs[q]->d_recv, ctxs[q]->n_recv))) return rc;
+    if ((rc = sum_over_contexts(ctxs, n, [](slimm_gpu_ctx *c) { return c->d_stats; }, (u64)ctxs[0]->G * 4))) return rc;
+    if ((rc = sum_over_contexts(ctxs, n, [](slimm_gpu_ctx *c) { return reinterpret_cast<u32 *>(&c->d_sc->n_reads); }, 4))) return rc;   // n_reads, n_uniq (u64 each; partial sums stay below 2^32)
+    for (u32 r = 0; r < n; ++r) {
+        if ((rc = slimm_gpu_set_global_hits(ctxs[r], global_hits))) return rc;
+        if ((rc = slimm_gpu_filter(ctxs[r], cov_cut_off, min_reads))) return rc;
+        if ((rc = slimm_gpu_assign(ctxs[r]))) return rc;
+    }
+    return sum_over_contexts(ctxs, n, [](slimm_gpu_ctx *c) { return c->d_assign; }, ctxs[0]->assign_words);
+}
+
 int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx)
 {
     if (!ctx) return SLIMM_GPU_EINVAL;

@@ -110,12 +110,17 @@ def test_cli_directory_mode(tmp_path):
     (d / "notes.txt").write_text("not an alignment file")
     out = tmp_path / "out"
     out.mkdir()
-    r = subprocess.run([native.CLI, "-d", "-o", str(out) + "/", os.path.join(c.path, "db.sldb"), str(d)], capture_output=True, text=True)
+    # a third sample against the same database with OTHER @SQ lines (fewer contigs): the context cannot be reused for it
+    q = gu.load_case("quirk")
+    (d / "c.sam").write_bytes(gzip.open(os.path.join(q.path, "in.sam.gz")).read())
+    r = subprocess.run([native.CLI, "-v", "-d", "-o", str(out) + "/", os.path.join(c.path, "db.sldb"), str(d)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     run = [x for x in gu.runs_of(c) if x.name == "default"][0]
     for base in ("a", "b"):
         gu.assert_profiles_match(os.path.join(run.path, "profile.tsv"), open(out / f"{base}_profile.tsv").read().splitlines())
-    assert "1820 SAM/BAM alignment records are proccessed." in r.stderr
+    assert os.path.exists(out / "c_profile.tsv")
+    # one GPU context per set of @SQ lines: a.sam creates it, b.sam reuses it (slimm_gpu_reset), c.sam needs a new one
+    assert r.stderr.count("(context reused)") == 1, r.stderr[-3000:]
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/slimm was not built (needs /root/reference at build time)")
@@ -140,3 +145,29 @@ def test_cli_against_reference_binary_side_by_side(args, tmp_path):
     compare_outputs(exp, got_out, "fresh", True)
     a, b = stderr_stats(rr.stderr, tmp_path), stderr_stats(rg.stderr, tmp_path)
     assert a == b and a["hits"] == "150000"
+
+
+def test_cli_two_gpus_give_the_single_gpu_profile(tmp_path):
+    """`slimm --gpus 2` (one host process, reads sharded over two devices, slimm_gpu_run_sharded_local): same _profile.tsv and
+    the same -v counters as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(4)
+    G = 1500
+    tax, accs = synth.make_taxonomy(G)
+    contigs = synth.make_contigs(G, rng, accs, 200_000, 900_000)
+    rec = synth.make_records(contigs, 1_200_000, rng, multi_frac=0.35, k_lo=2, k_hi=40, neigh=12)
+    sam = str(tmp_path / "s.sam")
+    synth.write_sam_for_records(sam, contigs, rec)
+    db = str(tmp_path / "db.sldb")
+    sldb.write_sldb(synth.database_for(tax), db)
+    outs = {}
+    for n in (1, 2):
+        out = str(tmp_path / f"out{n}")
+        os.makedirs(out)
+        r = subprocess.run([native.CLI, "-v", "-w", "10", "--gpus", str(n), "-o", out + "/", db, sam], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[n] = (open(os.path.join(out, "s_profile.tsv")).read(), stderr_stats(r.stderr, tmp_path))
+    assert outs[1][0] == outs[2][0]
+    assert outs[1][1] == outs[2][1] and outs[1][1]["hits"] == "1200000"
