@@ -439,8 +439,10 @@ __global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_bu
 // 16 warps per SM; 512 x 16: 32 warps per SM).
 template <bool PEER, int NT>
 __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2)
-k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, u32 *const *__restrict__ dest)
+k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, u32 *const *__restrict__ dest,
+        const u32 *__restrict__ n_ptr /* not null: the number of items lives on the device */)
 {
+    if (n_ptr) n = *n_ptr;
     constexpr int ITEMS = SPLIT_TILE / NT, NW = NT / 32;
     constexpr int SCAN_T = NT < MAX_BUCKETS ? NT : MAX_BUCKETS;    // threads that take part in the scan of the slice counts
     constexpr int HALVES = MAX_BUCKETS / SCAN_T;
@@ -550,6 +552,126 @@ k_peer_dest(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32 n_sl
         const u32 lo = (u32)((u64)n_slices * tid / n_ranks), hi = (u32)((u64)n_slices * (tid + 1) / n_ranks);
         if ((u64)(s[hi] - s[lo]) > recv_cap) atomicOr(overflow, 1u);
         if (tid == me) *n_recv = s[hi] - s[lo];
+    }
+}
+
+// ---- routed exchange (sharded runs, the default over NVLink) ---------------------------------------------------------
+// Peer stores of 80-byte runs (k_split<PEER>: a tile's share of ONE slice) use a third of the link.  Routed, a tile is only
+// partitioned by OWNER RANK: a rank's share of a tile is one contiguous kilobyte-sized segment, appended to the region the
+// receiver keeps for this source - full 128-byte stores.  The receiver then groups what it received by slice with the
+// local k_split (its runs are long: only the slices it owns occur), from slice totals it already knows from the all-gathered
+// counts.  k_peer_route_plan derives everything from that table on the device; no host round trip.
+#define ROUTE_MAX_RANKS 32
+struct RoutePlan {
+    u32 *dest[ROUTE_MAX_RANKS];      // where THIS rank's items for rank q start inside q's receive buffer
+    u32 cursor[ROUTE_MAX_RANKS];     // items appended so far (k_route)
+    unsigned char owner[MAX_BUCKETS];
+};
+
+__global__ void __launch_bounds__(MAX_BUCKETS)
+k_peer_route_plan(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32 n_slices, u32 n_ranks, u32 me, u32 *const *__restrict__ peer_recv,
+                  u64 recv_cap, RoutePlan *__restrict__ plan, Sched *__restrict__ local /* the receiver's split of what it gets */,
+                  u32 *__restrict__ n_recv, u32 *__restrict__ overflow)
+{
+    __shared__ u32 s[MAX_BUCKETS + 1];
+    __shared__ u32 s_from[ROUTE_MAX_RANKS][ROUTE_MAX_RANKS];       // [q][src]: items src sends to q
+    const u32 tid = threadIdx.x;
+    u32 q_of = 0;                                                  // owner of slice tid: slices [ns q / n, ns (q+1) / n)
+    if (tid < n_slices) while ((u64)n_slices * (q_of + 1) / n_ranks <= tid) ++q_of;
+    if (tid < n_slices) plan->owner[tid] = (unsigned char)q_of;
+    for (u32 i = tid; i < ROUTE_MAX_RANKS * ROUTE_MAX_RANKS; i += MAX_BUCKETS) (&s_from[0][0])[i] = 0;
+    __syncthreads();
+    u32 mine = 0;                                                  // items of slice tid this rank will hold (0 for slices it does not own)
+    if (tid < n_slices)
+        for (u32 src = 0; src < n_ranks; ++src) {
+            const u32 c = all_counts[(size_t)src * n_slices + tid];
+            if (c) atomicAdd(&s_from[q_of][src], c);
+            if (q_of == me) mine += c;
+        }
+    s[tid + 1] = mine;
+    if (tid == 0) s[0] = 0;
+    __syncthreads();
+    for (u32 d = 1; d < MAX_BUCKETS; d <<= 1) {                    // inclusive scan of s[1..]
+        const u32 t = tid + 1 > d ? s[tid + 1 - d] : 0;
+        __syncthreads();
+        s[tid + 1] += t;
+        __syncthreads();
+    }
+    local->cursor[tid] = local->start[tid] = s[tid];
+    local->count[tid] = mine;
+    if (tid == 0) { local->total_items = s[MAX_BUCKETS]; *n_recv = s[MAX_BUCKETS]; }
+    if (tid < n_ranks) {
+        u32 before = 0, all = 0;
+        for (u32 src = 0; src < n_ranks; ++src) { if (src < me) before += s_from[tid][src]; all += s_from[tid][src]; }
+        plan->dest[tid] = peer_recv[tid] + before;
+        plan->cursor[tid] = 0;
+        if ((u64)all > recv_cap) atomicOr(overflow, 1u);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+k_route(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_ranks, RoutePlan *__restrict__ plan)
+{
+    constexpr int ITEMS = SPLIT_TILE / NT, NW = NT / 32;
+    __shared__ u32 s_wcnt[NW][ROUTE_MAX_RANKS];                    // items of a (warp, rank) in this tile, then their tile-local start
+    __shared__ u32 s_seg[ROUTE_MAX_RANKS + 1];                     // tile-local start of every rank's segment
+    __shared__ u32 s_at[ROUTE_MAX_RANKS];                          // where the segment goes inside the receiver's region for this source
+    __shared__ u32 s_warp_tot[NW];
+    __shared__ unsigned char s_owner[MAX_BUCKETS];
+    __shared__ u32 s_item[SPLIT_TILE];
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (u32 b = tid; b < MAX_BUCKETS; b += NT) s_owner[b] = plan->owner[b];
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (u32 i = tid; i < NW * ROUTE_MAX_RANKS; i += NT) (&s_wcnt[0][0])[i] = 0;
+        __syncthreads();
+        const u64 t0 = tile * SPLIT_TILE;
+        u32 item[ITEMS], where[ITEMS];                             // where: rank << 16 | rank inside (tile, warp, rank)
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * NT + tid;
+            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            where[k] = 0xFFFFFFFFu;
+            if (item[k] != ITEM_SKIP) {
+                const u32 q = s_owner[(item[k] & 0x7FFFFFFFu) >> shift];
+                where[k] = (q << 16) | atomicAdd(&s_wcnt[wid][q], 1u);   // a warp's own counters: no contention between warps
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan over (rank major, warp minor): thread t <-> rank t / NW, warp t % NW
+            const u32 q = tid / NW, w = tid % NW;
+            const u32 v = q < n_ranks ? s_wcnt[w][q] : 0u;
+            u32 x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+            if (lane == 31) s_warp_tot[wid] = x;
+            __syncthreads();
+            u32 wbase = 0, all = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
+            const u32 excl = wbase + x - v;
+            if (q < n_ranks) { s_wcnt[w][q] = excl; if (w == 0) s_seg[q] = excl; }
+            if (tid == 0) s_seg[n_ranks] = all;
+        }
+        __syncthreads();
+        if (tid < n_ranks) {
+            const u32 len = s_seg[tid + 1] - s_seg[tid];
+            s_at[tid] = len ? atomicAdd(&plan->cursor[tid], len) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (where[k] != 0xFFFFFFFFu) s_item[s_wcnt[wid][where[k] >> 16] + (where[k] & 0xFFFFu)] = item[k];
+        __syncthreads();
+        for (u32 q = 0; q < n_ranks; ++q) {                        // a rank's segment: one contiguous run of full-width stores (peer memory over NVLink)
+            const u32 a = s_seg[q], b = s_seg[q + 1];
+            u32 *dst = plan->dest[q] + s_at[q];
+            for (u32 j = a + tid; j < b; j += NT) dst[j - a] = s_item[j];
+        }
+        __syncthreads();
     }
 }
 

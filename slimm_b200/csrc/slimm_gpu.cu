@@ -81,6 +81,8 @@ struct slimm_gpu_ctx {
     // peer-to-peer item exchange: every rank's receive buffer is mapped into every other rank (CUDA IPC over NVLink)
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
     u32 **d_dest = nullptr; u32 **d_peer_recv = nullptr; u32 *d_n_recv = nullptr;   // d_n_recv[0]: items this rank receives, [1]: a receive buffer would overflow
+    // routed exchange: a tile's share of a RANK travels as one segment, the receiver groups by slice (k_route, k_peer_route_plan)
+    RoutePlan *d_route = nullptr; Sched *d_sched2 = nullptr; u32 *d_recv2 = nullptr; u64 recv2_cap = 0; bool routed = false; int route_mode = 1;
     bool n_recv_on_device = false;          // the split was planned on the device (slimm_gpu_split_to_peers_device): n_recv lives there
     // slimm_gpu_push_packed: staging of the wire format + the running read-id counter
     u32 *d_pk_bits = nullptr; unsigned short *d_pk_ref16 = nullptr; u32 *d_pk_tiles = nullptr, *d_pk_counter = nullptr; u64 pk_cap = 0;
@@ -337,6 +339,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->stats_ready) cudaEventDestroy(ctx->stats_ready);
     if (ctx->fold_done) cudaEventDestroy(ctx->fold_done);
     cudaFree(ctx->d_cut_sorted); cudaFree(ctx->d_cut_prefix);
+    cudaFree(ctx->d_route); cudaFree(ctx->d_sched2); cudaFree(ctx->d_recv2);
     cudaFree(ctx->d_pk_bits); cudaFree(ctx->d_pk_ref16); cudaFree(ctx->d_pk_tiles); cudaFree(ctx->d_pk_counter);
     delete ctx;
     return SLIMM_GPU_OK;
@@ -415,7 +418,7 @@ int slimm_gpu_push_packed(slimm_gpu_ctx *ctx, const uint32_t *new_read_bits, con
     if (rc) return rc;
     if (ctx->pk_cap < n) {                    // the copy stream orders a refill behind the kernels that read the staging area
         CU(cudaStreamSynchronize(ctx->copy_stream));
-        cudaFree(ctx->d_pk_bits); cudaFree(ctx->d_pk_ref16); cudaFree(ctx->d_pk_tiles);
+    cudaFree(ctx->d_pk_bits); cudaFree(ctx->d_pk_ref16); cudaFree(ctx->d_pk_tiles);
         ctx->d_pk_bits = nullptr; ctx->d_pk_ref16 = nullptr; ctx->d_pk_tiles = nullptr; ctx->pk_cap = 0;
         CU(cudaMalloc(&ctx->d_pk_bits, (n + 31) / 32 * 4 + 4)); CU(cudaMalloc(&ctx->d_pk_ref16, n * 2 + 2));
         CU(cudaMalloc(&ctx->d_pk_tiles, ((n + UNPACK_TILE - 1) / UNPACK_TILE + 1) * 4));
@@ -524,9 +527,9 @@ static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * per_sm));
     (void)sgrid;
-    if (nt == 256) k_split<PEER, 256><<<grid, 256, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
-    else if (nt >= 1024) k_split<PEER, 1024><<<grid, 1024, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
-    else k_split<PEER, 512><<<grid, 512, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest);
+    if (nt == 256) k_split<PEER, 256><<<grid, 256, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
+    else if (nt >= 1024) k_split<PEER, 1024><<<grid, 1024, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
+    else k_split<PEER, 512><<<grid, 512, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
 }
 
 static bool aligned16(const RecSoA &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.ref) | ((uintptr_t)r.pos)) & 15u) == 0; }
@@ -859,7 +862,8 @@ static int accumulate_owned(slimm_gpu_ctx *ctx, const u32 *d_items, u64 n_items)
             CU(cudaMalloc(&ctx->d_fine, std::max<u64>(n_items + n_items / 8, 1024) * 4));
             ctx->fine_cap = n_items + n_items / 8;
         }
-        int rc = fine_accumulate(ctx, d_items, ctx->n_recv_on_device && d_items == ctx->d_recv ? ctx->d_n_recv : nullptr, n_items, n_items, ctx->d_fine, lo_bin, hi_bin);
+        int rc = fine_accumulate(ctx, d_items, ctx->n_recv_on_device && (d_items == ctx->d_recv || d_items == ctx->d_recv2) ? ctx->d_n_recv : nullptr, n_items, n_items,
+                                 ctx->d_fine, lo_bin, hi_bin);
         if (rc) return rc;
         ctx->shard_acc_done = true;
         return SLIMM_GPU_OK;
@@ -921,6 +925,8 @@ int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles, uint32_t 
     }
     if (!ctx->d_dest) CU(cudaMalloc(&ctx->d_dest, MAX_BUCKETS * sizeof(u32 *)));
     if (!ctx->d_n_recv) CU(cudaMalloc(&ctx->d_n_recv, 8));
+    if (!ctx->d_route) { CU(cudaMalloc(&ctx->d_route, sizeof(RoutePlan))); CU(cudaMalloc(&ctx->d_sched2, sizeof(Sched))); }
+    if (const char *e = getenv("SLIMM_PEER_ROUTE")) ctx->route_mode = atoi(e) != 0;
     cudaFree(ctx->d_peer_recv); ctx->d_peer_recv = nullptr;
     CU(cudaMalloc(&ctx->d_peer_recv, n_ranks * sizeof(u32 *)));
     CU(cudaMemcpy(ctx->d_peer_recv, ctx->peer_recv.data(), n_ranks * sizeof(u32 *), cudaMemcpyHostToDevice));
@@ -982,14 +988,28 @@ int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_co
     const u32 ns = n_slices_of(ctx);
     TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);
     CU(cudaMemsetAsync(ctx->d_n_recv, 0, 8, ctx->stream));
-    k_peer_dest<<<1, MAX_BUCKETS, 0, ctx->stream>>>(d_all_counts, ns, ctx->shard_n, ctx->shard_rank, ctx->d_peer_recv, ctx->recv_cap, ctx->d_dest, ctx->d_n_recv,
-                                                    ctx->d_n_recv + 1);
+    ctx->routed = ctx->route_mode == 1 && ctx->shard_n <= ROUTE_MAX_RANKS && ctx->acc_mode == 1;
+    if (ctx->routed) {
+        if (ctx->recv2_cap < ctx->recv_cap) {
+            cudaFree(ctx->d_recv2); ctx->d_recv2 = nullptr; ctx->recv2_cap = 0;
+            CU(cudaMalloc(&ctx->d_recv2, ctx->recv_cap * 4));
+            ctx->recv2_cap = ctx->recv_cap;
+        }
+        k_peer_route_plan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(d_all_counts, ns, ctx->shard_n, ctx->shard_rank, ctx->d_peer_recv, ctx->recv_cap, ctx->d_route,
+                                                              ctx->d_sched2, ctx->d_n_recv, ctx->d_n_recv + 1);
+    } else
+        k_peer_dest<<<1, MAX_BUCKETS, 0, ctx->stream>>>(d_all_counts, ns, ctx->shard_n, ctx->shard_rank, ctx->d_peer_recv, ctx->recv_cap, ctx->d_dest, ctx->d_n_recv,
+                                                        ctx->d_n_recv + 1);
     ctx->launches++;
     ctx->n_recv_on_device = true;
     ctx->n_recv = ctx->recv_cap;              // an upper bound for the host side (buffers, grids); the kernels read the count on the device
     if (ctx->split_pending) {
         const u32 n = (u32)ctx->n;
-        launch_k_split<true>(ctx, 0, ctx->d_items, n, ctx->bucket_shift, ns, nullptr, ctx->d_dest);
+        if (ctx->routed) {
+            const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
+            const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 2));
+            k_route<512><<<grid, 512, 0, ctx->stream>>>(ctx->d_items, n, ctx->bucket_shift, ctx->shard_n, ctx->d_route);
+        } else launch_k_split<true>(ctx, 0, ctx->d_items, n, ctx->bucket_shift, ns, nullptr, ctx->d_dest);
         ctx->launches++;
         ctx->split_pending = false;
     }
@@ -1079,6 +1099,19 @@ int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx)
 {
     if (!ctx) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_COVERAGE || !ctx->p2p) return fail(ctx, SLIMM_GPU_ESTATE, "accumulate_received belongs to a peer-to-peer sharded run, after split_to_peers");
+    if (ctx->routed && ctx->n_recv_on_device) {
+        // what arrived is grouped by source only: group it by slice (the slice totals came with the plan), then go on as usual
+        CU(cudaSetDevice(ctx->device));
+        const u64 n_tiles = (ctx->recv_cap + SPLIT_TILE - 1) / SPLIT_TILE;
+        const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 2));
+        {
+            TimeScope ts(ctx, SLIMM_GPU_T_SORT);   // (the sort slot of the timings is free in a sharded run: grouped input is required)
+            k_split<false, 512><<<grid, 512, 0, ctx->stream>>>(ctx->d_recv, 0, ctx->bucket_shift, n_slices_of(ctx), ctx->d_sched2, ctx->d_recv2, nullptr, ctx->d_n_recv);
+            ctx->launches++;
+        }
+        CU(cudaGetLastError());
+        return accumulate_owned(ctx, ctx->d_recv2, ctx->n_recv);
+    }
     return accumulate_owned(ctx, ctx->d_recv, ctx->n_recv);
 }
 
