@@ -415,6 +415,7 @@ def main():
     def timed(step_fn, n_warm, n_steps, collect_kernel=False):
         for _ in range(n_warm):
             step_fn()
+        phases.clear()                                        # (SLIMM_BENCH_PHASES) the timed steps only
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         kt = []
         barrier()
@@ -441,9 +442,18 @@ def main():
     launches = (gpu.launch_count() - launches0) // (warmup + args.steps) * args.steps
     ms_per_step = total_ms / args.steps
     value = wl["N"] / (ms_per_step * 1e-3)
+    phase_ms = {k: v / args.steps for k, v in phases.items()} if phases else None
     result = {"hits": summ.hits_count, "reads": summ.matches_count, "uniq": summ.uniq_matches_count,
               "uniq2": summ.uniq_matches_count2, "valid_refs": summ.n_valid, "rows": rows,
               "pairs": summ.n_pairs, "bins": summ.n_bins, "sorted_input": summ.input_was_sorted}
+
+    per_rank = None
+    if world > 1:                                             # every rank's kernel times (the line's own kernel_ms are rank 0's)
+        keys = sorted(ktimes[0])
+        mine = torch.tensor([statistics.mean(t[k] for t in ktimes) for k in keys], dtype=torch.float64, device=dev)
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank = {k: [round(float(a[i]), 3) for a in allk] for i, k in enumerate(keys) if any(float(a[i]) > 0 for a in allk)}
 
     # roofline: algorithmic bytes per kernel as in DESIGN.md section 3 (N*(16+16) + P*8 + U*8 + 16*B),
     # for this rank's share; the kernel with the largest share of the step is the one reported
@@ -600,12 +610,13 @@ def main():
             cpu = {"value": None, "unit": "records/s", "cores": 1, "kind": "unavailable", "sample": str(e)[:200]}
 
     if rank == 0:
-        if phases:
-            sys.stderr.write("phases (ms, summed over all resident + e2e steps incl. warm-up): " + json.dumps({k: round(v, 2) for k, v in phases.items()}) + "\n")
+        if phase_ms:
+            sys.stderr.write("phases (ms per timed resident step, rank 0): " + json.dumps({k: round(v, 3) for k, v in phase_ms.items()}) + "\n")
         line = dict(base)
         line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": int(launches),
                      "roofline": roofline, "cpu_baseline": cpu, "cli": dict(CLI_RESULT) or None, "clocks": clocks,
-                     "result": result, "exchange_used": ("p2p" if use_p2p else "nccl") if world > 1 else None})
+                     "result": result, "exchange_used": ("p2p" if use_p2p else "nccl") if world > 1 else None,
+                     "per_rank_kernel_ms": per_rank, "exchange_phases_ms": phase_ms})
         if equality is not None:
             line.update(equality)
         print(json.dumps(line), flush=True)
