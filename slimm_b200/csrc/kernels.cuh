@@ -723,6 +723,9 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 #define FINE_ITEMS 16               // items per thread of a k_fine_count / k_fine_split tile (16 measured faster than 32 here, 32 faster in k_split)
 #define FINE_TILE (256 * FINE_ITEMS)
 #define FINE_PRE 12               // items per thread k_fine_accumulate requests before it zero-fills its bins
+#ifndef FINE_PACKED_CTAS
+#define FINE_PACKED_CTAS 3          // CTAs per SM of the packed k_fine_accumulate (64 KB of shared memory each)
+#endif
 
 // first fine slice of the coarse slice the tile's first item belongs to
 __device__ __forceinline__ u32 fine_base(u32 first_item, u32 cshift) { return ((first_item & 0x7FFFFFFFu) >> cshift) << (cshift - FINE_SHIFT); }
@@ -876,7 +879,7 @@ k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n
 //           one CTA's fill / scan overlaps the other's item loads.  Launched for the slices with fewer than 65536 items;
 //   wide    two u32 per bin (128 KB, one CTA per SM) takes the others (or all of them, SLIMM_GPU_FINE=wide).
 template <bool PACKED, int NT>
-__global__ void __launch_bounds__(NT, PACKED ? 2 : 1)
+__global__ void __launch_bounds__(NT, PACKED ? FINE_PACKED_CTAS : 1)
 k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u32 f_lo, u32 f_hi, u64 Bp, const u64 *__restrict__ off, u32 G,
                   const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
                   u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket,

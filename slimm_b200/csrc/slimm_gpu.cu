@@ -499,7 +499,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
         u32 *ticket = ctx->d_fine_cnt + n_fine;                // two spare words behind the counts (zeroed with them): ticket, number of hot slices
         if (ctx->fine_packed) {
             // slices with fewer than 65536 items (all but the hottest): packed counters, two CTAs per SM; then the rest, wide
-            const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * 2);
+            const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * FINE_PACKED_CTAS);
             k_fine_accumulate<true, 512><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
                                                                                   ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr);
             const unsigned grid1 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
