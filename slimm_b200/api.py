@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "slimm_gpu_accumulate_items", "slimm_gpu_stats_device", "slimm_gpu_profile_failed",
     "slimm_gpu_p2p_reserve", "slimm_gpu_p2p_connect", "slimm_gpu_split_to_peers", "slimm_gpu_accumulate_received", "slimm_gpu_p2p_disable",
     "slimm_gpu_slice_counts_device", "slimm_gpu_split_to_peers_device", "slimm_gpu_push_packed",
+    "slimm_gpu_run_sharded_local",
 ]
 
 

@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <cuda/barrier>
 #include <stdint.h>
 
 typedef uint32_t u32;
@@ -552,6 +553,96 @@ k_peer_dest(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32 n_sl
         const u32 lo = (u32)((u64)n_slices * tid / n_ranks), hi = (u32)((u64)n_slices * (tid + 1) / n_ranks);
         if ((u64)(s[hi] - s[lo]) > recv_cap) atomicOr(overflow, 1u);
         if (tid == me) *n_recv = s[hi] - s[lo];
+    }
+}
+
+// The same multisplit with the tile brought in by the bulk-copy engine (cp.async.bulk, completion on an mbarrier) and double
+// buffered: while a tile is ranked, ordered and copied out, the next 32 KB are already on their way into shared memory, and no
+// register holds an item while it waits for DRAM (16 ranks per thread are all that stays live).  Local splits only.
+#define SPLITB_NT 512
+#define SPLITB_SMEM (2 * SPLIT_TILE * 4 + SPLIT_TILE * 4)      // two raw tiles + the ordered tile (dynamic shared memory)
+__global__ void __launch_bounds__(SPLITB_NT, 2)
+k_split_bulk(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, const u32 *__restrict__ n_ptr)
+{
+    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
+    constexpr int NT = SPLITB_NT, ITEMS = SPLIT_TILE / NT, NW = NT / 32;
+    extern __shared__ __align__(128) u32 sb_dyn[];
+    u32 *const raw0 = sb_dyn, *const raw1 = sb_dyn + SPLIT_TILE, *const s_item = sb_dyn + 2 * SPLIT_TILE;
+    __shared__ u32 s_cnt[MAX_BUCKETS];
+    __shared__ u32 s_delta[MAX_BUCKETS];
+    __shared__ u32 s_warp_tot[NW];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ barrier_t bar[2];
+    if (n_ptr) n = *n_ptr;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        init(&bar[0], NT); init(&bar[1], NT);
+        cuda::device::experimental::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE, n_full = (u64)n / SPLIT_TILE;   // tiles, whole tiles (bulk copies)
+    barrier_t::arrival_token tok0, tok1;
+    // every thread arrives on the buffer's barrier when its copy is issued (thread 0 adds the bytes to expect) and waits on it
+    // when the tile is needed
+    auto issue = [&](u64 tile, u32 *dst, barrier_t &b) -> barrier_t::arrival_token {
+        if (tile >= n_full) return b.arrive();                   // the last, partial tile is loaded by the threads themselves
+        if (tid == 0) {
+            cuda::device::experimental::fence_proxy_async_shared_cta();   // the buffer's earlier readers come first
+            cuda::device::memcpy_async_tx(dst, items + tile * SPLIT_TILE, cuda::aligned_size_t<16>(SPLIT_TILE * 4), b);
+            return cuda::device::barrier_arrive_tx(b, 1, SPLIT_TILE * 4);
+        }
+        return b.arrive();
+    };
+    u64 tile = blockIdx.x;
+    if (tile < n_tiles) tok0 = issue(tile, raw0, bar[0]);
+    for (u32 it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const bool odd = it & 1;
+        u32 *const raw = odd ? raw1 : raw0;
+        const u64 next = tile + gridDim.x;
+        if (next < n_tiles) { if (odd) tok0 = issue(next, raw0, bar[0]); else tok1 = issue(next, raw1, bar[1]); }
+        for (u32 b = tid; b < MAX_BUCKETS; b += NT) s_cnt[b] = 0;
+        if (odd) bar[1].wait(std::move(tok1)); else bar[0].wait(std::move(tok0));
+        const u64 t0 = tile * SPLIT_TILE;
+        if (tile >= n_full) {                                    // partial tile
+            for (u32 j = tid; j < SPLIT_TILE; j += NT) raw[j] = t0 + j < n ? __ldcs(items + t0 + j) : ITEM_SKIP;
+        }
+        __syncthreads();
+        u32 where[ITEMS];                                        // slice << 16 | rank inside (tile, slice)
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 v = raw[k * NT + tid];
+            where[k] = 0xFFFFFFFFu;
+            if (v != ITEM_SKIP) {
+                const u32 bk = (v & 0x7FFFFFFFu) >> shift;
+                where[k] = (bk << 16) | atomicAdd(&s_cnt[bk], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the slice counts over the tile: one slice per thread
+        const u32 tot = tid < n_buckets ? s_cnt[tid] : 0u;
+        u32 x = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
+        if (lane == 31) s_warp_tot[wid] = x;
+        __syncthreads();
+        u32 wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; total += t; }
+        const u32 excl = wbase + x - tot;
+        if (tid < n_buckets) {
+            s_cnt[tid] = excl;
+            if (tot) s_delta[tid] = atomicAdd(&sd->cursor[tid], tot) - excl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (where[k] != 0xFFFFFFFFu) s_item[s_cnt[where[k] >> 16] + (where[k] & 0xFFFFu)] = raw[k * NT + tid];
+        __syncthreads();
+        for (u32 j = tid; j < total; j += NT) {                  // the slice of an item is a function of the item
+            const u32 v = s_item[j];
+            out[j + s_delta[(v & 0x7FFFFFFFu) >> shift]] = v;
+        }
+        __syncthreads();
     }
 }
 

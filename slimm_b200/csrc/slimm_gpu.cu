@@ -527,6 +527,14 @@ static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * per_sm));
     (void)sgrid;
+    static const int bulk = getenv("SLIMM_SPLIT_BULK") ? atoi(getenv("SLIMM_SPLIT_BULK")) : 1;   // tiles through the bulk-copy engine (local splits)
+    if (!PEER && bulk && ((uintptr_t)items & 15) == 0 && n_buckets <= SPLITB_NT) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_split_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLITB_SMEM); attr = true; }
+        const int bgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 2));
+        k_split_bulk<<<bgrid, SPLITB_NT, SPLITB_SMEM, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, nullptr);
+        return;
+    }
     if (nt == 256) k_split<PEER, 256><<<grid, 256, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
     else if (nt >= 1024) k_split<PEER, 1024><<<grid, 1024, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
     else k_split<PEER, 512><<<grid, 512, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
