@@ -9,7 +9,7 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${R}_cfg5.js
 timeout 600 python bench.py --steps 5 --warmup 3 --bins skip --no-cpu-baseline > gpurun_out/bench_${R}_cfg5_skipbins.json 2> gpurun_out/bench_${R}_cfg5_skipbins.err; echo "bench cfg5 skip rc=$?"
 timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 > gpurun_out/bench_${R}_cfg2.json 2> gpurun_out/bench_${R}_cfg2.err; echo "bench cfg2 rc=$?"
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_${R}_reference.json 2> gpurun_out/bench_${R}_reference.err; echo "bench reference rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/launches_${R}.log 2>&1; echo "launch list rc=$?"
 WORKLOADS="cfg5 cfg2" bash scripts/gpu_traffic.sh $R
 KERNELS="k_coverage k_fine_accumulate k_assign_reads" bash scripts/gpu_ncu.sh $R

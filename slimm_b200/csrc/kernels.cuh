@@ -438,7 +438,37 @@ __global__ void __launch_bounds__(MAX_BUCKETS) k_bucket_scan(Sched *sd, u32 n_bu
 // run happens inside the split, tile by tile, as plain stores.
 // NT threads x (SPLIT_TILE / NT) items: the same tile with fewer registers per thread buys resident warps (256 x 32: 92 registers,
 // 16 warps per SM; 512 x 16: 32 warps per SM).
-template <bool PEER, int NT>
+// a tile's items into registers: 128-bit loads for whole tiles of an aligned array
+template <int NT, int ITEMS>
+__device__ __forceinline__ void load_tile(const u32 *__restrict__ items, u64 t0, u32 n, bool vec, u32 tid, u32 (&item)[ITEMS])
+{
+    if (vec && t0 + (u64)NT * ITEMS <= n) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(items + t0) + tid;
+#pragma unroll
+        for (int k = 0; k < ITEMS / 4; ++k) {
+            const uint4 v = __ldcs(p + k * NT);
+            item[4 * k] = v.x; item[4 * k + 1] = v.y; item[4 * k + 2] = v.z; item[4 * k + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * NT + tid;
+            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
+        }
+    }
+}
+
+// Branch-free ranking: ITEM_SKIP (repeat hits, the padding of the last tile) is ranked too, in a slot of its own - slot
+// min(0x7FFFFFFF >> shift, MAX_BUCKETS), which lies beyond the slices in use unless the bins reach the last 2^shift below 2^31
+// (EXACT then tests for ITEM_SKIP explicitly) - and staged behind the tile's other items, where the copy loop never looks.
+template <bool EXACT>
+__device__ __forceinline__ u32 split_slot(u32 item, u32 shift)
+{
+    if (EXACT) return item == ITEM_SKIP ? (u32)MAX_BUCKETS : (item & 0x7FFFFFFFu) >> shift;
+    return min((item << 1) >> (shift + 1), (u32)MAX_BUCKETS);
+}
+
+template <bool PEER, int NT, bool EXACT>
 __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2)
 k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *sd, u32 *__restrict__ out, u32 *const *__restrict__ dest,
         const u32 *__restrict__ n_ptr /* not null: the number of items lives on the device */)
@@ -447,30 +477,25 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
     constexpr int ITEMS = SPLIT_TILE / NT, NW = NT / 32;
     constexpr int SCAN_T = NT < MAX_BUCKETS ? NT : MAX_BUCKETS;    // threads that take part in the scan of the slice counts
     constexpr int HALVES = MAX_BUCKETS / SCAN_T;
-    __shared__ u32 s_cnt[MAX_BUCKETS];         // items of each slice in this tile, then the slice's tile-local start
+    __shared__ u32 s_cnt[MAX_BUCKETS + 1];     // items of each slice in this tile (+ the slot of ITEM_SKIP), then the slice's tile-local start
     __shared__ u32 s_delta[MAX_BUCKETS];       // global start - tile-local start (mod 2^32)
     __shared__ u32 *s_dst[PEER ? MAX_BUCKETS : 1];   // PEER: destination of the slice's first item of this tile, minus the tile-local start
     __shared__ u32 s_item[SPLIT_TILE];
     __shared__ u32 s_warp_tot[NW];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool vec = (reinterpret_cast<uintptr_t>(items) & 15) == 0;
+    const u32 skip_slot = EXACT ? (u32)MAX_BUCKETS : min(0x7FFFFFFFu >> shift, (u32)MAX_BUCKETS);
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (u32 b = tid; b < MAX_BUCKETS; b += NT) s_cnt[b] = 0;
+        for (u32 b = tid; b <= MAX_BUCKETS; b += NT) s_cnt[b] = 0;
         __syncthreads();
         const u64 t0 = tile * SPLIT_TILE;
-        u32 item[ITEMS], where[ITEMS];                         // where: slice << 16 | rank inside (tile, slice)
+        u32 item[ITEMS], where[ITEMS];                         // where: slot << 16 | rank inside (tile, slot)
+        load_tile<NT, ITEMS>(items, t0, n, vec, tid, item);
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
-            const u64 i = t0 + (u64)k * NT + tid;
-            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
-        }
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            where[k] = 0xFFFFFFFFu;
-            if (item[k] != ITEM_SKIP) {
-                const u32 bk = (item[k] & 0x7FFFFFFFu) >> shift;
-                where[k] = (bk << 16) | atomicAdd(&s_cnt[bk], 1u);
-            }
+            const u32 bk = split_slot<EXACT>(item[k], shift);
+            where[k] = (bk << 16) | atomicAdd(&s_cnt[bk], 1u);
         }
         __syncthreads();
         // exclusive scan of the slice counts over the tile (HALVES slices per scanning thread, halves in order)
@@ -503,20 +528,23 @@ k_split(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_buckets, Sched *s
                 }
             }
         }
+        if (tid == 0) s_cnt[skip_slot] = base;                 // ITEM_SKIP is staged behind the items
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k)
-            if (where[k] != 0xFFFFFFFFu) {
-                const u32 bk = where[k] >> 16;
-                const u32 pos = s_cnt[bk] + (where[k] & 0xFFFFu);
-                s_item[pos] = item[k];
-            }
+        for (int k = 0; k < ITEMS; ++k) s_item[s_cnt[where[k] >> 16] + (where[k] & 0xFFFFu)] = item[k];
         __syncthreads();
         const u32 total = base;                                // items of this tile (thread-uniform)
-        for (u32 j = tid; j < total; j += NT) {                // the slice of an item is a function of the item
-            const u32 v = s_item[j], bk = (v & 0x7FFFFFFFu) >> shift;
-            if (PEER) s_dst[bk][j] = v; else out[j + s_delta[bk]] = v;
-        }
+        if (!PEER && total == SPLIT_TILE) {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const u32 j = k * NT + tid, v = s_item[j];
+                out[j + s_delta[(v << 1) >> (shift + 1)]] = v;
+            }
+        } else
+            for (u32 j = tid; j < total; j += NT) {            // the slice of an item is a function of the item
+                const u32 v = s_item[j], bk = (v << 1) >> (shift + 1);
+                if (PEER) s_dst[bk][j] = v; else out[j + s_delta[bk]] = v;
+            }
         __syncthreads();
     }
 }
@@ -821,73 +849,138 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 // first fine slice of the coarse slice the tile's first item belongs to
 __device__ __forceinline__ u32 fine_base(u32 first_item, u32 cshift) { return ((first_item & 0x7FFFFFFFu) >> cshift) << (cshift - FINE_SHIFT); }
 
+// index of an item's fine slice relative to the tile's first one, clamped to FINE_REL (the overflow slot: items of a tile that
+// spans more than FINE_REL fine slices, and ITEM_SKIP).  Fast form: one shift-and-subtract, one shift, one minimum - the
+// difference is taken modulo 2^17, which is exact as long as there are at most FINE_WRAP_SAFE fine slices (a slice BEFORE the
+// tile's first one, and ITEM_SKIP, then still land beyond FINE_REL); EXACT: the plain 32-bit difference and an explicit test.
+#define FINE_WRAP_SAFE ((1u << 17) - FINE_REL)
+template <bool EXACT>
+__device__ __forceinline__ u32 fine_rel(u32 item, u32 base, u32 neg_base_shl /* 0 - (base << (FINE_SHIFT + 1)) */)
+{
+    if (EXACT) return item == ITEM_SKIP ? (u32)FINE_REL : min(((item & 0x7FFFFFFFu) >> FINE_SHIFT) - base, (u32)FINE_REL);
+    return min(((item << 1) + neg_base_shl) >> (FINE_SHIFT + 1), (u32)FINE_REL);
+}
+
+template <bool EXACT>
 __global__ void __launch_bounds__(256)
 k_fine_count(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr /* number of items on the device, or null: n_given */, u32 n_given, u32 cshift,
              u32 *__restrict__ fine_cnt)
 {
-    __shared__ u32 s_cnt[FINE_REL];
+    __shared__ u32 s_cnt[FINE_REL + 1];
     const u32 n = n_ptr ? *n_ptr : n_given;
     const u32 tid = threadIdx.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(items) & 15) == 0;
     const u64 n_tiles = ((u64)n + FINE_TILE - 1) / FINE_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (u32 b = tid; b < FINE_REL; b += 256) s_cnt[b] = 0;
+        for (u32 b = tid; b <= FINE_REL; b += 256) s_cnt[b] = 0;
         __syncthreads();
         const u64 t0 = tile * FINE_TILE;
-        const u32 base = fine_base(__ldg(items + t0), cshift);
+        const u32 base = fine_base(__ldg(items + t0), cshift), nbs = 0u - (base << (FINE_SHIFT + 1));
         u32 item[FINE_ITEMS];
+        load_tile<256, FINE_ITEMS>(items, t0, n, vec, tid, item);
 #pragma unroll
-        for (int k = 0; k < FINE_ITEMS; ++k) {
-            const u64 i = t0 + (u64)k * 256 + tid;
-            item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
-        }
-#pragma unroll
-        for (int k = 0; k < FINE_ITEMS; ++k)
-            if (item[k] != ITEM_SKIP) {
-                const u32 f = (item[k] & 0x7FFFFFFFu) >> FINE_SHIFT;
-                if (f - base < FINE_REL) atomicAdd(&s_cnt[f - base], 1u);
-                else atomicAdd(fine_cnt + f, 1u);
-            }
+        for (int k = 0; k < FINE_ITEMS; ++k) atomicAdd(&s_cnt[fine_rel<EXACT>(item[k], base, nbs)], 1u);
         __syncthreads();
+        if (s_cnt[FINE_REL]) {                                   // rare: a tile over more than two coarse slices (or the last, partial tile)
+#pragma unroll
+            for (int k = 0; k < FINE_ITEMS; ++k)
+                if (item[k] != ITEM_SKIP && fine_rel<EXACT>(item[k], base, nbs) == FINE_REL) atomicAdd(fine_cnt + ((item[k] & 0x7FFFFFFFu) >> FINE_SHIFT), 1u);
+        }
         for (u32 b = tid; b < FINE_REL; b += 256)
             if (s_cnt[b]) atomicAdd(fine_cnt + base + b, s_cnt[b]);
         __syncthreads();
     }
 }
 
-// start[f] = cursor[f] = items before fine slice f; start[n_fine] = all items.  One block.
-// Also lists the HOT slices (65536 items or more: the ones the packed accumulate leaves to the wide one) in hot[0 .. *n_hot).
-__global__ void __launch_bounds__(1024)
-k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor, u32 *__restrict__ hot, u32 *__restrict__ n_hot)
+// start[f] = cursor[f] = items before fine slice f; start[n_fine] = all items.  One cluster of FINE_SCAN_CL CTAs: every warp
+// owns a contiguous chunk of the counts - chunk totals first, exchanged through distributed shared memory, then the scan with
+// the totals of the chunks before as carry; a lane takes 16 consecutive counts per step with 128-bit loads and stores (the
+// stores of one SM alone would take longer than everything else: eight SMs share them).
+// Also lists the HOT slices (65536 items or more: the ones the packed accumulate leaves to the wide one) in hot[0 .. *n_hot) and the
+// VERY hot ones (FINE_VHOT items or more: a cluster of CTAs shares each of them) in vhot[0 .. *n_vhot) instead.
+#define FINE_VHOT (1u << 19)
+#define FINE_SCAN_CL 8
+__global__ void __cluster_dims__(FINE_SCAN_CL, 1, 1) __launch_bounds__(1024)
+k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor, u32 *__restrict__ hot, u32 *__restrict__ n_hot,
+            u32 *__restrict__ vhot, u32 *__restrict__ n_vhot)
 {
+    namespace cg = cooperative_groups;
     __shared__ u32 s_warp[32];
-    __shared__ u32 s_run;
-    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_run = 0;
-    __syncthreads();
-    for (u32 f0 = 0; f0 < n_fine; f0 += 1024) {
-        const u32 f = f0 + tid;
-        const u32 v = f < n_fine ? cnt[f] : 0u;
-        u32 x = v;
+    cg::cluster_group cl = cg::this_cluster();
+    const u32 r = cl.block_rank();
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, gw = r * 32 + wid;
+    const u32 per = (((n_fine + 32 * FINE_SCAN_CL - 1) / (32 * FINE_SCAN_CL)) + 511) & ~511u;    // counts per warp, a multiple of 512
+    const u32 lo = (u32)min((u64)n_fine, (u64)gw * per), hi = (u32)min((u64)n_fine, (u64)lo + per);
+    const bool vec = ((reinterpret_cast<uintptr_t>(cnt) | reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(cursor)) & 15) == 0;
+    u32 sum = 0;
+    for (u32 f0 = lo; f0 < hi; f0 += 512) {
+        const u32 f = f0 + 16 * lane;
+        if (vec && f + 16 <= hi) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cnt + f) + k); sum += q.x + q.y + q.z + q.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (f + k < hi) sum += __ldg(cnt + f + k);
+        }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_warp[wid] = sum;
+    cl.sync();
+    u32 run = 0;                                                 // items before my chunk: the warps before mine, in every CTA up to mine
+#pragma unroll
+    for (u32 q = 0; q < FINE_SCAN_CL; ++q)
+        if (q < r || (q == r && lane < wid)) run += *(cl.map_shared_rank(s_warp, q) + lane);
+    run = warp_sum(run);
+    cl.sync();                                                   // nobody reads my totals any more
+    for (u32 f0 = lo; f0 < hi; f0 += 512) {
+        const u32 f = f0 + 16 * lane;
+        const bool whole = vec && f + 16 <= hi;
+        u32 v[16];
+        if (whole) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cnt + f) + k);
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = f + k < hi ? __ldg(cnt + f + k) : 0u;
+        }
+        u32 mine = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mine += v[k];
+        u32 x = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        u32 wbase = 0, all = 0;
+        u32 e[16];
+        e[0] = run + x - mine;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) { const u32 t = s_warp[k]; if (k < (int)wid) wbase += t; all += t; }
-        const u32 run = s_run;
-        if (f < n_fine) {
-            const u32 e = run + wbase + x - v;
-            start[f] = e; cursor[f] = e;
-            if (v >= 65536u) hot[atomicAdd(n_hot, 1u)] = f;    // at most 2^16 of them (fewer than 2^32 items)
+        for (int k = 1; k < 16; ++k) e[k] = e[k - 1] + v[k - 1];
+        if (whole) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 q = make_uint4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+                reinterpret_cast<uint4 *>(start + f)[k] = q;
+                reinterpret_cast<uint4 *>(cursor + f)[k] = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (f + k < hi) { start[f + k] = e[k]; cursor[f + k] = e[k]; }
         }
-        __syncthreads();
-        if (tid == 0) s_run = run + all;
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (v[k] >= 65536u) {                                // (v is 0 beyond hi)  at most 2^16 hot slices (fewer than 2^32 items)
+                if (v[k] >= FINE_VHOT && vhot) vhot[atomicAdd(n_vhot, 1u)] = f + k;
+                else hot[atomicAdd(n_hot, 1u)] = f + k;
+            }
+        run += __shfl_sync(FULL, x, 31);
     }
-    if (tid == 0) start[n_fine] = s_run;
+    if (gw == 32 * FINE_SCAN_CL - 1 && lane == 31) start[n_fine] = run;   // the last warp's carry ends up as the total (its chunk may be empty)
 }
 
+// (A branch-free form of this kernel - every item ranked through the tables with an overflow slot, as k_fine_count and k_split
+// do - executes 28 % fewer instructions and is 7 % SLOWER, ncu r2m: the kernel is bound by shared-memory wavefronts (atomics,
+// scatter into the staging tile, bucket look-ups: l1tex 73-77 %), and the bursts of sixteen atomics per thread fill the MIO queue.)
 __global__ void __launch_bounds__(256)
 k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
              u32 *__restrict__ out)
@@ -975,7 +1068,8 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                   const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
                   u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket,
                   u32 min_cnt, u32 max_cnt /* this launch takes the slices with min_cnt <= items < max_cnt */,
-                  const u32 *__restrict__ hot, const u32 *__restrict__ n_hot /* not null: walk this list of slices instead of all of them */)
+                  const u32 *__restrict__ hot, const u32 *__restrict__ n_hot /* not null: walk this list of slices instead of all of them */,
+                  u32 *__restrict__ hist16 /* PACKED, not null: the bins of these slices are kept as {cov:16 | uniq_cov:16} words (half the bytes) */)
 {
     extern __shared__ u32 sh[];                                // PACKED: bins[FINE_BINS]; wide: cov[FINE_BINS] | uniq_cov[FINE_BINS]
     __shared__ u32 s_next;
@@ -987,11 +1081,11 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
     const u32 n_list = hot ? *n_hot : 0u;
     u32 idx = blockIdx.x;                                      // list mode: my position in the list
     for (u32 f = hot ? (idx < n_list ? hot[idx] : f_hi) : f_lo + blockIdx.x; f < f_hi;) {
-        if (!hot && tid == 0) s_next = f_lo + gridDim.x + atomicAdd(ticket, 1u);   // the next slice's ticket travels while this one is worked on
+        if (tid == 0) s_next = (hot ? 0u : f_lo) + gridDim.x + atomicAdd(ticket, 1u);   // the next slice's ticket travels while this one is worked on (list mode: the next list position)
         const u32 lo = __ldg(start + f), hi = __ldg(start + f + 1);
         const u32 cnt = hi - lo;
         const bool mine = cnt >= min_cnt && cnt < max_cnt;
-        if (mine && (cnt || hist4)) {                          // an empty slice only matters when somebody reads the bins
+        if (mine && (cnt || hist4 || hist16)) {                // an empty slice only matters when somebody reads the bins
             // the first items of every thread are requested first of all: their DRAM latency hides behind the reference lookup
             // and the zero-fill of the bins
             const u32 *my_items = fine + lo + tid;
@@ -1044,6 +1138,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                     for (int t = 0; t < 8; ++t) {
                         if (PACKED) {
                             const uint2 w2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64);
+                            if (hist16 && (u32)(h * 8 + t) < my_steps) __stcs(reinterpret_cast<uint2 *>(hist16 + (step0 + h * 8 + t) * 64) + lane, w2);
                             v[t] = make_uint4(w2.x & 0xFFFFu, w2.x >> 16, w2.y & 0xFFFFu, w2.y >> 16);
                         } else {
                             const uint2 c2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64),
@@ -1051,7 +1146,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                             v[t] = make_uint4(c2.x, u2.x, c2.y, u2.y);
                         }
                     }
-                    if (hist4) {
+                    if (hist4 && !(PACKED && hist16)) {
                         uint4 *dst = hist4 + (step0 + h * 8) * 32 + lane;
 #pragma unroll
                         for (int t = 0; t < 8; ++t) if ((u32)(h * 8 + t) < my_steps) __stcs(dst + t * 32, v[t]);
@@ -1086,9 +1181,79 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
             }
         }
         __syncthreads();                                       // everybody is done with the bins; s_next is visible
-        if (hot) { idx += gridDim.x; f = idx < n_list ? hot[idx] : f_hi; }
+        if (hot) { idx = s_next; f = idx < n_list ? hot[idx] : f_hi; }
         else f = s_next;
         __syncthreads();
+    }
+}
+
+// The VERY hot fine slices (FINE_VHOT items or more; lognormal communities put millions of items on the slices of their top
+// genomes) would each keep one CTA busy long after the rest of the GPU has finished.  Here a cluster of FINE_CL CTAs shares a
+// slice: every CTA applies its share of the items to a private copy of the bins (wide counters, 128 KB), the copies are summed
+// through distributed shared memory - CTA r of the cluster sums bins [r, r+1) * FINE_BINS / FINE_CL of all copies into its own -
+// and every CTA reduces the statistics of and writes out its own share of the bins.  The list is walked cluster by cluster.
+#define FINE_CL 8
+__global__ void __cluster_dims__(FINE_CL, 1, 1) __launch_bounds__(1024, 1)
+k_fine_accumulate_cluster(const u32 *__restrict__ fine, const u32 *__restrict__ start, u64 Bp, const u64 *__restrict__ off, u32 G,
+                          const u32 *__restrict__ fine_ref, u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */,
+                          const u32 *__restrict__ vhot, const u32 *__restrict__ n_vhot)
+{
+    namespace cg = cooperative_groups;
+    extern __shared__ u32 sh[];                                // cov[FINE_BINS] | uniq_cov[FINE_BINS]
+    constexpr u32 NT = 1024, SHARE = FINE_BINS / FINE_CL;      // bins a CTA sums, reduces and writes
+    constexpr u32 TAKE = NT * 8;                               // items a CTA takes at a time
+    static_assert(SHARE == 64 * (NT / 32), "one 64-bin step per warp");
+    cg::cluster_group cl = cg::this_cluster();
+    const u32 r = cl.block_rank(), cid = blockIdx.x / FINE_CL, n_cl = gridDim.x / FINE_CL;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u64 n_steps = Bp >> 6;
+    const u32 n_list = *n_vhot;
+    for (u32 idx = cid; idx < n_list; idx += n_cl) {
+        const u32 f = vhot[idx];
+        const u32 lo = __ldg(start + f), cnt = __ldg(start + f + 1) - lo;
+        for (u32 k = tid; k < 2 * FINE_BINS / 4; k += NT) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        for (u32 i0 = r * TAKE; i0 < cnt; i0 += FINE_CL * TAKE) {
+            u32 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = i0 + k * NT + tid < cnt ? __ldcs(fine + lo + i0 + k * NT + tid) : ITEM_SKIP;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (v[k] != ITEM_SKIP) {
+                    const u32 b = v[k] & (FINE_BINS - 1);
+                    atomicAdd(&sh[b], 1u);
+                    if (v[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u);
+                }
+        }
+        cl.sync();                                             // every copy is complete
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                          // cov, uniq_cov
+#pragma unroll
+            for (u32 w0 = 0; w0 < SHARE; w0 += NT) {
+                const u32 w = h * FINE_BINS + r * SHARE + w0 + tid;
+                u32 a = sh[w];
+#pragma unroll
+                for (u32 q = 1; q < FINE_CL; ++q) a += *(cl.map_shared_rank(sh, (r + q) % FINE_CL) + w);
+                sh[w] = a;
+            }
+        }
+        cl.sync();                                             // nobody reads my copy any more; my share is summed
+        const u64 step = (((u64)f << FINE_SHIFT) >> 6) + r * (SHARE / 64) + wid;      // my warp's 64 bins
+        if (step < n_steps) {
+            const u64 first_bin = step << 6;
+            u32 a = __ldg(fine_ref + f), b = min(__ldg(fine_ref + f + 1) + 1u, G);    // largest g in [a, b) with off[g] <= my first bin
+            while (b - a > 1) { const u32 mid = (a + b) >> 1; if (__ldg(off + mid) <= first_bin) a = mid; else b = mid; }
+            const u32 wb = r * SHARE + wid * 64 + 2 * lane;    // lane l holds bins 2l, 2l+1 of the step
+            const uint2 c2 = *reinterpret_cast<const uint2 *>(sh + wb), u2 = *reinterpret_cast<const uint2 *>(sh + FINE_BINS + wb);
+            if (hist4) __stcs(hist4 + step * 32 + lane, make_uint4(c2.x, u2.x, c2.y, u2.y));
+            const u32 nz = warp_sum((c2.x != 0) + (c2.y != 0)), sum = warp_sum(c2.x + c2.y);
+            const u32 unz = warp_sum((u2.x != 0) + (u2.y != 0)), usum = warp_sum(u2.x + u2.y);
+            if (lane == 0 && (nz | unz)) {
+                atomicAdd(stats + 4 * a + 0, nz); atomicAdd(stats + 4 * a + 1, sum);
+                if (unz) { atomicAdd(stats + 4 * a + 2, unz); atomicAdd(stats + 4 * a + 3, usum); }
+            }
+        }
+        __syncthreads();                                       // my bins are read before the next slice zero-fills them
     }
 }
 
@@ -1154,9 +1319,16 @@ __global__ void k_cov2_nz(const u32 *__restrict__ cov2, const u64 *__restrict__ 
 
 // uniq_cov2 starts as uniq_cov of the surviving references (a read with one target whose reference
 // survives stays unique); k_assign adds the reads that BECAME unique.  One warp step = 64 bins.
+// compact storage of a fine-slice run: which layout holds this bin (see k_extract_bins_compact)
+__device__ __forceinline__ bool fine_slice_is_wide(const u32 *__restrict__ fine_start, u64 bin)
+{
+    const u32 f = (u32)(bin >> FINE_SHIFT);
+    return __ldg(fine_start + f + 1) - __ldg(fine_start + f) >= 65536u;
+}
 __global__ void __launch_bounds__(256)
 k_cov2_base(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict__ off, u32 G,
-            const u32 *__restrict__ valid_bits, uint2 *__restrict__ cov2_2)
+            const u32 *__restrict__ valid_bits, uint2 *__restrict__ cov2_2,
+            const u32 *__restrict__ hist16 /* not null: compact storage (see k_extract_bins_compact) */, const u32 *__restrict__ fine_start)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1167,8 +1339,13 @@ k_cov2_base(const uint4 *__restrict__ hist4, u64 n_steps, const u64 *__restrict_
         while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (__ldg(off + mid) <= bin0) lo = mid; else hi = mid; }
         uint2 o = make_uint2(0, 0);
         if ((__ldg(valid_bits + (lo >> 5)) >> (lo & 31)) & 1u) {
-            const uint4 v = __ldg(hist4 + s * 32 + lane);
-            o = make_uint2(v.y, v.w);
+            if (hist16 && !fine_slice_is_wide(fine_start, bin0)) {
+                const uint2 w2 = __ldg(reinterpret_cast<const uint2 *>(hist16 + bin0) + lane);
+                o = make_uint2(w2.x >> 16, w2.y >> 16);
+            } else {
+                const uint4 v = __ldg(hist4 + s * 32 + lane);
+                o = make_uint2(v.y, v.w);
+            }
         }
         cov2_2[s * 32 + lane] = o;
     }
@@ -2070,6 +2247,18 @@ __global__ void k_pack_values(const u32 *__restrict__ ref, const i32 *__restrict
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = make_uint2(ref[i], (u32)pos[i]);
+}
+
+// the bins of fine-slice runs with compact storage: slices with fewer than 65536 items live in hist16 as {cov:16 | uniq_cov:16},
+// the hot ones in the interleaved 64-bit histogram
+__global__ void k_extract_bins_compact(const u32 *__restrict__ hist64, const u32 *__restrict__ hist16, const u32 *__restrict__ fine_start, u64 first, u32 word,
+                                       u32 nb, u32 *__restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const u64 b = first + i;
+    if (fine_slice_is_wide(fine_start, b)) out[i] = hist64[b * 2 + word];
+    else { const u32 w = hist16[b]; out[i] = word ? w >> 16 : w & 0xFFFFu; }
 }
 
 __global__ void k_extract_bins(const u32 *__restrict__ src, u64 first, u32 stride_words, u32 word, u32 nb, u32 *__restrict__ out)

@@ -39,6 +39,8 @@ struct slimm_gpu_ctx {
     cudaTextureObject_t meta2_tex = 0; int cov_gather = 0;   // 1: meta2 through the texture path in k_coverage_tile (default; SLIMM_COV_GATHER=ldg: plain loads)
     uint4 *d_meta = nullptr; uint2 *d_meta2 = nullptr; u32 *d_lin = nullptr; u32 *d_top_idx = nullptr; u64 *d_off = nullptr;
     unsigned long long *d_hist = nullptr; u32 *d_cov2 = nullptr;
+    u32 *d_hist16 = nullptr; u64 hist16_cap = 0;   // compact bins {cov:16 | uniq_cov:16} of the fine slices with fewer than 65536 items (fine-slice runs)
+    bool hist_compact = false, compact_bins = true;   // this run's bins are in the compact layout; SLIMM_GPU_COMPACT_BINS=0: always the interleaved 64-bit histogram
     u32 *d_stats = nullptr; float *d_cp = nullptr; u32 *d_scratch = nullptr;
     u32 *d_valid_bits = nullptr; unsigned char *d_valid_bytes = nullptr;
     u32 *d_assign = nullptr; u64 assign_words = 0;
@@ -92,6 +94,7 @@ struct slimm_gpu_ctx {
     u32 *d_fine_cnt = nullptr, *d_fine_start = nullptr, *d_fine_cursor = nullptr, *d_fine = nullptr, *d_fine_ref = nullptr, *d_fine_hot = nullptr; u64 fine_slices_cap = 0, fine_cap = 0;
     int acc_mode = 1;                       // 1: fine slices in shared memory, 0: 64-bit REDs into L2-resident slices
     bool fine_packed = true;                // slices with fewer than 65536 items use 16+16-bit counters (64 KB per CTA)
+    bool fine_cluster = true;               // slices with FINE_VHOT items or more are shared by a cluster of CTAs (SLIMM_GPU_FINE_CLUSTER=0: one CTA each)
     bool stats_done = false;                // the accumulate stage already reduced the per-reference statistics
     bool shard_acc_done = false;
     int tail_mode = -1;                     // -1 auto (device reduction when the database allows), 1 general host path
@@ -180,6 +183,7 @@ static int layout_bins(slimm_gpu_ctx *ctx)
     const u64 Bp = ctx->h_off[G];
     if (Bp != ctx->Bp || !ctx->d_hist) {
         if (ctx->d_hist) cudaFree(ctx->d_hist);
+        cudaFree(ctx->d_hist16); ctx->d_hist16 = nullptr; ctx->hist16_cap = 0;
         if (ctx->d_cov2) cudaFree(ctx->d_cov2);
         ctx->d_hist = nullptr; ctx->d_cov2 = nullptr;
         CU(cudaMalloc(&ctx->d_hist, std::max<u64>(Bp, 64) * 8));
@@ -276,8 +280,11 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     if (const char *e = getenv("SLIMM_GPU_ACC")) ctx->acc_mode = !strcmp(e, "l2") ? 0 : 1;
     if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "SLIMM_GPU_SKIP_BINS and SLIMM_GPU_KEEP_UNIQ_COV2 exclude each other");
     CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
     CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
     if (const char *e = getenv("SLIMM_GPU_FINE")) ctx->fine_packed = strcmp(e, "wide") != 0;
+    if (const char *e = getenv("SLIMM_GPU_FINE_CLUSTER")) ctx->fine_cluster = atoi(e) != 0;
+    if (const char *e = getenv("SLIMM_GPU_COMPACT_BINS")) ctx->compact_bins = atoi(e) != 0;
     if (const char *e = getenv("SLIMM_GPU_COV")) ctx->cov_variant = !strcmp(e, "window") ? 0 : 1;
     if (G < 65536) {
         // per level, the dense index of every distinct taxon id (zeros included): equal indices <=> equal ids
@@ -320,7 +327,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     free_records(ctx);
     if (ctx->meta2_tex) cudaDestroyTextureObject(ctx->meta2_tex);
-    cudaFree(ctx->d_meta); cudaFree(ctx->d_meta2); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist);
+    cudaFree(ctx->d_meta); cudaFree(ctx->d_meta2); cudaFree(ctx->d_off); cudaFree(ctx->d_lin); cudaFree(ctx->d_top_idx); cudaFree(ctx->d_hist); cudaFree(ctx->d_hist16);
     cudaFree(ctx->d_cov2); cudaFree(ctx->d_stats); cudaFree(ctx->d_cp); cudaFree(ctx->d_scratch); cudaFree(ctx->d_valid_bits);
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
@@ -474,21 +481,25 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     if (ctx->fine_slices_cap < n_fine) {
         cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor);
         ctx->d_fine_cnt = ctx->d_fine_start = ctx->d_fine_cursor = nullptr; ctx->fine_slices_cap = 0;
-        CU(cudaMalloc(&ctx->d_fine_cnt, (n_fine + 2) * 4)); CU(cudaMalloc(&ctx->d_fine_start, (n_fine + 1) * 4));
+        CU(cudaMalloc(&ctx->d_fine_cnt, (n_fine + 8) * 4)); CU(cudaMalloc(&ctx->d_fine_start, (n_fine + 1) * 4));
         CU(cudaMalloc(&ctx->d_fine_cursor, (n_fine + 1) * 4));
         ctx->fine_slices_cap = n_fine;
     }
-    if (!ctx->d_fine_hot) CU(cudaMalloc(&ctx->d_fine_hot, 65536 * 4));   // slices with >= 65536 items: fewer than 2^16 of them
+    if (!ctx->d_fine_hot) CU(cudaMalloc(&ctx->d_fine_hot, 2 * 65536 * 4));   // slices with >= 65536 items: fewer than 2^16 of them; second half: the very hot ones
     TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
-    CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 2) * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 8) * 4, ctx->stream));
+    const bool exact = n_fine > FINE_WRAP_SAFE;               // (bins within 2^23 of 2^31: the kernels take the plain 32-bit slice difference)
+    // spare words behind the counts (zeroed with them): ticket of the packed pass, number of hot slices, ticket of the hot pass, number of very hot slices
+    u32 *ticket = ctx->d_fine_cnt + n_fine, *n_hot = ticket + 1, *hot_ticket = ticket + 2, *n_vhot = ticket + 3;
+    u32 *vhot = ctx->fine_cluster && ctx->fine_packed ? ctx->d_fine_hot + 65536 : nullptr;
     CU(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->G * 16, ctx->stream));
     const u64 n_tiles = (n_cap + FINE_TILE - 1) / FINE_TILE;
     if (n_tiles) {
         const int cgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 8));
-        k_fine_count<<<cgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
+        if (exact) k_fine_count<true><<<cgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
+        else k_fine_count<false><<<cgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cnt);
     }
-    k_fine_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot,
-                                             ctx->d_fine_cnt + n_fine + 1);
+    k_fine_scan<<<FINE_SCAN_CL, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot, n_hot, vhot, n_vhot);
     if (n_tiles) {
         const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
         k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
@@ -496,20 +507,40 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
         uint4 *hist4 = (ctx->flags & SLIMM_GPU_SKIP_BINS) ? nullptr : (uint4 *)ctx->d_hist;
-        u32 *ticket = ctx->d_fine_cnt + n_fine;                // two spare words behind the counts (zeroed with them): ticket, number of hot slices
+        // compact bins: the slices of the packed pass keep their 16+16-bit words (4 instead of 8 bytes per bin written); the hot slices
+        // go to the interleaved 64-bit histogram as before; readers tell the two by the slice's item count (k_extract_bins_compact)
+        u32 *hist16 = nullptr;
+        ctx->hist_compact = false;
+        if (hist4 && ctx->fine_packed && ctx->compact_bins) {
+            if (ctx->hist16_cap < ctx->Bp) {
+                cudaFree(ctx->d_hist16); ctx->d_hist16 = nullptr; ctx->hist16_cap = 0;
+                CU(cudaMalloc(&ctx->d_hist16, std::max<u64>(ctx->Bp, 64) * 4));
+                ctx->hist16_cap = ctx->Bp;
+            }
+            hist16 = ctx->d_hist16;
+            ctx->hist_compact = true;
+        }
         if (ctx->fine_packed) {
             // slices with fewer than 65536 items (all but the hottest): packed counters, two CTAs per SM; then the rest, wide
             const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * FINE_PACKED_CTAS);
             k_fine_accumulate<true, 512><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr);
+                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr, hist16);
+            // the hot slices k_fine_scan listed: wide counters, one CTA per slice (list positions handed out by a ticket); the very hot
+            // ones: a cluster of CTAs per slice
             const unsigned grid1 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
             k_fine_accumulate<false, 1024><<<grid1, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 65536u, 0xFFFFFFFFu, ctx->d_fine_hot, ticket + 1);   // walks the list of hot slices k_fine_scan left
+                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, hot_ticket, 65536u, 0xFFFFFFFFu, ctx->d_fine_hot, n_hot, nullptr);
             ctx->launches++;
+            if (vhot) {
+                const unsigned n_cl = std::max(1u, (unsigned)ctx->sm_count / FINE_CL - 2u);
+                k_fine_accumulate_cluster<<<n_cl * FINE_CL, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, ctx->Bp, ctx->d_off, ctx->G, ctx->d_fine_ref,
+                                                                                                 ctx->d_stats, hist4, vhot, n_vhot);
+                ctx->launches++;
+            }
         } else {
             const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
             k_fine_accumulate<false, 1024><<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu, nullptr, nullptr);
+                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu, nullptr, nullptr, nullptr);
         }
     }
     ctx->launches += 4;
@@ -517,6 +548,9 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     ctx->stats_done = true;
     return SLIMM_GPU_OK;
 }
+
+// ITEM_SKIP is ranked in the slot min(0x7FFFFFFF >> shift, MAX_BUCKETS); when the slices in use reach that slot the kernels test for it explicitly
+static bool split_needs_exact(u32 shift, u32 n_buckets) { return std::min<u32>(0x7FFFFFFFu >> shift, MAX_BUCKETS) < n_buckets; }
 
 // K1b: shape of the split CTAs (SLIMM_SPLIT_NT = 256 | 512 | 1024 threads over the same 8192-item tile)
 template <bool PEER>
@@ -527,7 +561,7 @@ static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * per_sm));
     (void)sgrid;
-    static const int bulk = getenv("SLIMM_SPLIT_BULK") ? atoi(getenv("SLIMM_SPLIT_BULK")) : 1;   // tiles through the bulk-copy engine (local splits)
+    static const int bulk = getenv("SLIMM_SPLIT_BULK") ? atoi(getenv("SLIMM_SPLIT_BULK")) : 0;   // tiles through the bulk-copy engine (local splits)
     if (!PEER && bulk && ((uintptr_t)items & 15) == 0 && n_buckets <= SPLITB_NT) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_split_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLITB_SMEM); attr = true; }
@@ -535,9 +569,16 @@ static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 
         k_split_bulk<<<bgrid, SPLITB_NT, SPLITB_SMEM, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, nullptr);
         return;
     }
-    if (nt == 256) k_split<PEER, 256><<<grid, 256, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
-    else if (nt >= 1024) k_split<PEER, 1024><<<grid, 1024, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
-    else k_split<PEER, 512><<<grid, 512, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);
+    const bool exact = split_needs_exact(shift, n_buckets);
+#define SLIMM_SPLIT_LAUNCH(NT_)                                                                                                                   \
+    do {                                                                                                                                          \
+        if (exact) k_split<PEER, NT_, true><<<grid, NT_, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);           \
+        else k_split<PEER, NT_, false><<<grid, NT_, 0, ctx->stream>>>(items, n, shift, n_buckets, ctx->d_sched, out, dest, nullptr);                \
+    } while (0)
+    if (nt == 256) SLIMM_SPLIT_LAUNCH(256);
+    else if (nt >= 1024) SLIMM_SPLIT_LAUNCH(1024);
+    else SLIMM_SPLIT_LAUNCH(512);
+#undef SLIMM_SPLIT_LAUNCH
 }
 
 static bool aligned16(const RecSoA &r) { return ((((uintptr_t)r.rid) | ((uintptr_t)r.ref) | ((uintptr_t)r.pos)) & 15u) == 0; }
@@ -765,6 +806,7 @@ int slimm_gpu_coverage(slimm_gpu_ctx *ctx)
     if (!ctx) return SLIMM_GPU_EINVAL;
     if (ctx->stage != ST_CREATED) return fail(ctx, SLIMM_GPU_ESTATE, "coverage already ran; call slimm_gpu_reset for a new sample");
     CU(cudaSetDevice(ctx->device));
+    ctx->hist_compact = false;                                  // set again by the fine-slice accumulate when it keeps compact bins
     // kernels wait for the uploads without blocking the host
     CU(cudaEventRecord(ctx->upload_done, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
@@ -789,6 +831,7 @@ int slimm_gpu_bins_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32)
 {
     if (!ctx || !d_ptr || !n_u32) return SLIMM_GPU_EINVAL;
     if (ctx->flags & SLIMM_GPU_SKIP_BINS) return fail(ctx, SLIMM_GPU_EINVAL, "the bins are not kept (SLIMM_GPU_SKIP_BINS)");
+    if (ctx->hist_compact) return fail(ctx, SLIMM_GPU_ESTATE, "the bins of this run are kept in the compact per-slice layout: use slimm_gpu_fetch_bins (or SLIMM_GPU_COMPACT_BINS=0)");
     *d_ptr = ctx->d_hist; *n_u32 = ctx->Bp * 2;
     return SLIMM_GPU_OK;
 }
@@ -1114,7 +1157,10 @@ int slimm_gpu_accumulate_received(slimm_gpu_ctx *ctx)
         const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 2));
         {
             TimeScope ts(ctx, SLIMM_GPU_T_SORT);   // (the sort slot of the timings is free in a sharded run: grouped input is required)
-            k_split<false, 512><<<grid, 512, 0, ctx->stream>>>(ctx->d_recv, 0, ctx->bucket_shift, n_slices_of(ctx), ctx->d_sched2, ctx->d_recv2, nullptr, ctx->d_n_recv);
+            if (split_needs_exact(ctx->bucket_shift, n_slices_of(ctx)))
+                k_split<false, 512, true><<<grid, 512, 0, ctx->stream>>>(ctx->d_recv, 0, ctx->bucket_shift, n_slices_of(ctx), ctx->d_sched2, ctx->d_recv2, nullptr, ctx->d_n_recv);
+            else
+                k_split<false, 512, false><<<grid, 512, 0, ctx->stream>>>(ctx->d_recv, 0, ctx->bucket_shift, n_slices_of(ctx), ctx->d_sched2, ctx->d_recv2, nullptr, ctx->d_n_recv);
             ctx->launches++;
         }
         CU(cudaGetLastError());
@@ -1171,7 +1217,8 @@ int slimm_gpu_filter(slimm_gpu_ctx *ctx, float cov_cut_off, uint32_t min_reads)
         if (ctx->d_cov2 && ctx->Bp) {   // uniq_cov2 starts as uniq_cov of the surviving references
             const u64 n_steps = ctx->Bp / 64;
             k_cov2_base<<<grid_for(ctx, n_steps * 32, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)ctx->d_hist, n_steps, ctx->d_off, ctx->G,
-                                                                                     ctx->d_valid_bits, (uint2 *)ctx->d_cov2);
+                                                                                     ctx->d_valid_bits, (uint2 *)ctx->d_cov2,
+                                                                                     ctx->hist_compact ? ctx->d_hist16 : nullptr, ctx->d_fine_start);
             ctx->launches++;
         }
         CU(cudaGetLastError());
@@ -1394,7 +1441,11 @@ int slimm_gpu_fetch_bins(slimm_gpu_ctx *ctx, int which, uint32_t ref, uint32_t *
         ctx->tmp_bins_cap = nb;
     }
     const u32 *src = which == 2 ? ctx->d_cov2 : (const u32 *)ctx->d_hist;
-    k_extract_bins<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(src, ctx->h_off[ref], which == 2 ? 1 : 2, which == 1 ? 1 : 0, nb, ctx->d_tmp_bins);
+    if (which != 2 && ctx->hist_compact)
+        k_extract_bins_compact<<<(nb + 255) / 256, 256, 0, ctx->stream>>>((const u32 *)ctx->d_hist, ctx->d_hist16, ctx->d_fine_start, ctx->h_off[ref], which == 1 ? 1 : 0, nb,
+                                                                         ctx->d_tmp_bins);
+    else
+        k_extract_bins<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(src, ctx->h_off[ref], which == 2 ? 1 : 2, which == 1 ? 1 : 0, nb, ctx->d_tmp_bins);
     ctx->launches++;
     CU(cudaMemcpyAsync(out, ctx->d_tmp_bins, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -93,6 +93,7 @@ def test_cfg5_shaped_fine_bins():
     bins = padded[r64] + np.minimum(pos.astype(np.int64) + 50, contigs.lengths.astype(np.int64)[r64]) // w
     per_fine = np.bincount(bins >> 14, minlength=(int(padded[-1]) >> 14) + 1)
     assert (per_fine >= 65536).any() and (per_fine == 0).any() and ((per_fine > 0) & (per_fine < 65536)).any()
+    assert (per_fine >= (1 << 19)).any() and ((per_fine >= 65536) & (per_fine < (1 << 19))).any()     # cluster-shared and single-CTA hot slices
     del bins, r64
     taxa = {t: v for t, v in db.taxid__name.items()}
     with api.SlimmGpu(contigs.lengths, lineage, w, 100) as gpu:

@@ -263,13 +263,16 @@ def test_skip_bins_profile_only_run():
         api.SlimmGpu(contigs.lengths, lineage, w, 100, flags=api.SKIP_BINS | api.KEEP_UNIQ_COV2)
 
 
-def test_hot_fine_slice():
+@pytest.mark.parametrize("n_records", [400_000, 1_500_000])
+def test_hot_fine_slice(n_records):
     """All records in one fine slice (a few short references): more than 65535 items per slice, so the packed 16+16-bit
-    counters do not apply and the wide shared-memory variant runs; bins included."""
-    contigs, rec, lineage = _synthetic(4, 400_000, 8, len_lo=2000, len_hi=5000, multi_frac=0.5, k_lo=2, k_hi=3, neigh=2)
+    counters do not apply and the wide shared-memory variant runs; with 2^19 items or more a cluster of CTAs shares the
+    slice (private copies of the bins summed through distributed shared memory); bins included."""
+    contigs, rec, lineage = _synthetic(4, n_records, 8, len_lo=2000, len_hi=5000, multi_frac=0.5, k_lo=2, k_hi=3, neigh=2)
     w = 5
     res = oracle.run(contigs.lengths, lineage, w, 100, 0.95, rec.read_id, rec.ref_id, rec.begin_pos)
     assert res.n_pairs > 65536 and int(res.bin_off[-1]) < 16384
+    assert (res.n_pairs >= (1 << 19)) == (n_records > 1_000_000)
     with api.SlimmGpu(contigs.lengths, lineage, w, 100) as gpu:
         gpu.set_scatter_mode(1)
         gpu.push(rec.read_id, rec.ref_id, rec.begin_pos)
