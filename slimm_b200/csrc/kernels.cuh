@@ -841,6 +841,7 @@ k_accumulate(const u32 *__restrict__ grouped, const Sched *__restrict__ sd, unsi
 #define FINE_REL MAX_BUCKETS      // fine slices covered by a tile's shared-memory tables
 #define FINE_ITEMS 16               // items per thread of a k_fine_count / k_fine_split tile (16 measured faster than 32 here, 32 faster in k_split)
 #define FINE_TILE (256 * FINE_ITEMS)
+#define FINE_REF_BLOCK 1024u       // fine_ref holds the reference of the first bin of every block of this many bins
 #define FINE_PRE 12               // items per thread k_fine_accumulate requests before it zero-fills its bins
 #ifndef FINE_PACKED_CTAS
 #define FINE_PACKED_CTAS 3          // CTAs per SM of the packed k_fine_accumulate (64 KB of shared memory each)
@@ -981,30 +982,35 @@ k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u3
 // (A branch-free form of this kernel - every item ranked through the tables with an overflow slot, as k_fine_count and k_split
 // do - executes 28 % fewer instructions and is 7 % SLOWER, ncu r2m: the kernel is bound by shared-memory wavefronts (atomics,
 // scatter into the staging tile, bucket look-ups: l1tex 73-77 %), and the bursts of sixteen atomics per thread fill the MIO queue.)
-__global__ void __launch_bounds__(256)
+// NT threads x ITEMS items per tile (256 x 16, or 512 x 16: longer runs per fine slice and half as many tiles)
+template <int NT, int ITEMS>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 4)
 k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
              u32 *__restrict__ out)
 {
+    constexpr int TILE = NT * ITEMS, NW = NT / 32;
+    constexpr int SCAN_T = NT < FINE_REL ? NT : FINE_REL;      // threads that take part in the scan of the bucket counts
+    constexpr int HALVES = FINE_REL / SCAN_T;
     __shared__ u32 s_cnt[FINE_REL];            // items of each fine slice in this tile, then the slice's tile-local start
     __shared__ u32 s_delta[FINE_REL];          // global start - tile-local start (mod 2^32)
-    __shared__ u32 s_item[FINE_TILE];
-    __shared__ u32 s_warp_tot[8];
+    __shared__ u32 s_item[TILE];
+    __shared__ u32 s_warp_tot[NW];
     const u32 n = n_ptr ? *n_ptr : n_given;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const u64 n_tiles = ((u64)n + FINE_TILE - 1) / FINE_TILE;
+    const u64 n_tiles = ((u64)n + TILE - 1) / TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (u32 b = tid; b < FINE_REL; b += 256) s_cnt[b] = 0;
+        for (u32 b = tid; b < FINE_REL; b += NT) s_cnt[b] = 0;
         __syncthreads();
-        const u64 t0 = tile * FINE_TILE;
+        const u64 t0 = tile * TILE;
         const u32 base = fine_base(__ldg(items + t0), cshift);
-        u32 item[FINE_ITEMS], where[FINE_ITEMS];             // where: bucket << 16 | rank inside (tile, bucket)
+        u32 item[ITEMS], where[ITEMS];                       // where: bucket << 16 | rank inside (tile, bucket)
 #pragma unroll
-        for (int k = 0; k < FINE_ITEMS; ++k) {
-            const u64 i = t0 + (u64)k * 256 + tid;
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 i = t0 + (u64)k * NT + tid;
             item[k] = i < n ? __ldcs(items + i) : ITEM_SKIP;
         }
 #pragma unroll
-        for (int k = 0; k < FINE_ITEMS; ++k) {
+        for (int k = 0; k < ITEMS; ++k) {
             where[k] = 0xFFFFFFFFu;
             if (item[k] != ITEM_SKIP) {
                 const u32 f = (item[k] & 0x7FFFFFFFu) >> FINE_SHIFT;
@@ -1013,12 +1019,12 @@ k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n
             }
         }
         __syncthreads();
-        // exclusive scan of the bucket counts over the tile (two buckets per thread, halves in order)
-        u32 tot[2], excl[2], run = 0;
+        // exclusive scan of the bucket counts over the tile (HALVES buckets per scanning thread, halves in order)
+        u32 tot[HALVES], excl[HALVES], run = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const u32 b = tid + h * 256;
-            tot[h] = s_cnt[b];
+        for (int h = 0; h < HALVES; ++h) {
+            const u32 b = tid + h * SCAN_T;
+            tot[h] = tid < SCAN_T ? s_cnt[b] : 0u;
             u32 x = tot[h];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, x, o); if ((int)lane >= o) x += y; }
@@ -1026,20 +1032,22 @@ k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n
             __syncthreads();
             u32 wbase = 0, all = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
+            for (int k = 0; k < SCAN_T / 32; ++k) { const u32 t = s_warp_tot[k]; if (k < (int)wid) wbase += t; all += t; }
             excl[h] = run + wbase + x - tot[h];
             run += all;
             __syncthreads();
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const u32 b = tid + h * 256;
-            s_cnt[b] = excl[h];
-            if (tot[h]) s_delta[b] = atomicAdd(cursor + base + b, tot[h]) - excl[h];
+        for (int h = 0; h < HALVES; ++h) {
+            const u32 b = tid + h * SCAN_T;
+            if (tid < SCAN_T) {
+                s_cnt[b] = excl[h];
+                if (tot[h]) s_delta[b] = atomicAdd(cursor + base + b, tot[h]) - excl[h];
+            }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < FINE_ITEMS; ++k)
+        for (int k = 0; k < ITEMS; ++k)
             if (where[k] != 0xFFFFFFFFu) {
                 const u32 bk = where[k] >> 16;
                 const u32 pos = s_cnt[bk] + (where[k] & 0xFFFFu);
@@ -1047,7 +1055,7 @@ k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n
             }
         __syncthreads();
         const u32 total = run;                                 // items of this tile that went through the tables
-        for (u32 j = tid; j < total; j += 256) {
+        for (u32 j = tid; j < total; j += NT) {
             const u32 v = s_item[j];
             out[j + s_delta[((v & 0x7FFFFFFFu) >> FINE_SHIFT) - base]] = v;
         }
@@ -1062,15 +1070,15 @@ k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n
 //           65536 items (no counter can reach 2^16) - every slice but the hottest few; 64 KB per CTA, two CTAs per SM, so
 //           one CTA's fill / scan overlaps the other's item loads.  Launched for the slices with fewer than 65536 items;
 //   wide    two u32 per bin (128 KB, one CTA per SM) takes the others (or all of them, SLIMM_GPU_FINE=wide).
-template <bool PACKED, int NT>
+template <bool PACKED, int NT, bool COMPACT /* PACKED only: hist4 is the array of {cov:16 | uniq_cov:16} words (half the bytes) */>
 __global__ void __launch_bounds__(NT, PACKED ? FINE_PACKED_CTAS : 1)
 k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u32 f_lo, u32 f_hi, u64 Bp, const u64 *__restrict__ off, u32 G,
-                  const u32 *__restrict__ fine_ref /* [n_fine + 1]: the reference that holds the first bin of every fine slice */,
+                  const u32 *__restrict__ fine_ref /* the reference that holds the first bin of every block of FINE_REF_BLOCK bins */,
                   u32 *__restrict__ stats, uint4 *__restrict__ hist4 /* nullptr: bins are not kept */, u32 *__restrict__ ticket,
                   u32 min_cnt, u32 max_cnt /* this launch takes the slices with min_cnt <= items < max_cnt */,
-                  const u32 *__restrict__ hot, const u32 *__restrict__ n_hot /* not null: walk this list of slices instead of all of them */,
-                  u32 *__restrict__ hist16 /* PACKED, not null: the bins of these slices are kept as {cov:16 | uniq_cov:16} words (half the bytes) */)
+                  const u32 *__restrict__ hot, const u32 *__restrict__ n_hot /* not null: walk this list of slices instead of all of them */)
 {
+    static_assert(PACKED || !COMPACT, "compact bins are the packed counters as they are");
     extern __shared__ u32 sh[];                                // PACKED: bins[FINE_BINS]; wide: cov[FINE_BINS] | uniq_cov[FINE_BINS]
     __shared__ u32 s_next;
     constexpr u32 WORDS = PACKED ? FINE_BINS : 2 * FINE_BINS;
@@ -1085,7 +1093,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
         const u32 lo = __ldg(start + f), hi = __ldg(start + f + 1);
         const u32 cnt = hi - lo;
         const bool mine = cnt >= min_cnt && cnt < max_cnt;
-        if (mine && (cnt || hist4 || hist16)) {                // an empty slice only matters when somebody reads the bins
+        if (mine && (cnt || hist4)) {                          // an empty slice only matters when somebody reads the bins
             // the first items of every thread are requested first of all: their DRAM latency hides behind the reference lookup
             // and the zero-fill of the bins
             const u32 *my_items = fine + lo + tid;
@@ -1099,32 +1107,50 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
             u32 g = 0;
             u64 g_end = 0;
             if (cnt && my_steps) {
-                u32 a = __ldg(fine_ref + f), b = min(__ldg(fine_ref + f + 1) + 1u, G);   // largest g in [a, b) with off[g] <= my first bin
                 const u64 first_bin = step0 << 6;
+                u32 a = __ldg(fine_ref + first_bin / FINE_REF_BLOCK), b = min(__ldg(fine_ref + first_bin / FINE_REF_BLOCK + 1) + 1u, G);   // largest g in [a, b) with off[g] <= my first bin
                 while (b - a > 1) { const u32 mid = (a + b) >> 1; if (__ldg(off + mid) <= first_bin) a = mid; else b = mid; }
                 g = a;
                 g_end = __ldg(off + g + 1);
             }
             for (u32 k = tid; k < WORDS / 4; k += NT) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-#pragma unroll
-            for (int k = 0; k < PRE; ++k)
-                if (pre[k] != ITEM_SKIP) {
-                    const u32 b = pre[k] & (FINE_BINS - 1);
-                    if (PACKED) atomicAdd(&sh[b], (pre[k] >> 31) ? 0x10001u : 1u);
-                    else { atomicAdd(&sh[b], 1u); if (pre[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u); }
+            // the items beyond the first PRE per thread arrive TB per thread at a time; in the wide kernel a batch is requested before
+            // the one before it is applied: a hot slice streams its items with 2 x TB loads per thread in flight instead of waiting for
+            // DRAM once per batch (it was bound by exactly that: 4 loads per thread and round trip = 1.6 TB/s over 148 SMs, launch list r2o)
+            constexpr int TB = PACKED ? 4 : 12;
+            auto apply = [&](u32 it) {
+                if (it != ITEM_SKIP) {
+                    const u32 b = it & (FINE_BINS - 1);
+                    if (PACKED) atomicAdd(&sh[b], (it >> 31) ? 0x10001u : 1u);
+                    else { atomicAdd(&sh[b], 1u); if (it >> 31) atomicAdd(&sh[FINE_BINS + b], 1u); }
                 }
-            for (u32 i0 = PRE * NT; i0 < cnt; i0 += 4 * NT) {      // a slice with more items than usual
-                u32 v[4];
+            };
+            if (PACKED) {                                          // (no registers to spare at three CTAs per SM: one batch at a time)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = i0 + k * NT + tid < cnt ? __ldcs(my_items + i0 + k * NT) : ITEM_SKIP;
+                for (int k = 0; k < PRE; ++k) apply(pre[k]);
+                for (u32 i0 = PRE * NT; i0 < cnt; i0 += TB * NT) { // a slice with more items than usual
+                    u32 v[TB];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (v[k] != ITEM_SKIP) {
-                        const u32 b = v[k] & (FINE_BINS - 1);
-                        if (PACKED) atomicAdd(&sh[b], (v[k] >> 31) ? 0x10001u : 1u);
-                        else { atomicAdd(&sh[b], 1u); if (v[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u); }
-                    }
+                    for (int k = 0; k < TB; ++k) v[k] = i0 + k * NT + tid < cnt ? __ldcs(my_items + i0 + k * NT) : ITEM_SKIP;
+#pragma unroll
+                    for (int k = 0; k < TB; ++k) apply(v[k]);
+                }
+            } else {
+                u32 v[TB];
+#pragma unroll
+                for (int k = 0; k < TB; ++k) v[k] = (u32)(PRE + k) * NT + tid < cnt ? __ldcs(my_items + (PRE + k) * NT) : ITEM_SKIP;
+#pragma unroll
+                for (int k = 0; k < PRE; ++k) apply(pre[k]);
+                for (u32 i0 = PRE * NT; i0 < cnt; i0 += TB * NT) {
+                    u32 nx[TB];
+#pragma unroll
+                    for (int k = 0; k < TB; ++k) nx[k] = i0 + (TB + k) * NT + tid < cnt ? __ldcs(my_items + i0 + (TB + k) * NT) : ITEM_SKIP;
+#pragma unroll
+                    for (int k = 0; k < TB; ++k) apply(v[k]);
+#pragma unroll
+                    for (int k = 0; k < TB; ++k) v[k] = nx[k];
+                }
             }
             __syncthreads();
             if (my_steps) {
@@ -1138,7 +1164,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                     for (int t = 0; t < 8; ++t) {
                         if (PACKED) {
                             const uint2 w2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64);
-                            if (hist16 && (u32)(h * 8 + t) < my_steps) __stcs(reinterpret_cast<uint2 *>(hist16 + (step0 + h * 8 + t) * 64) + lane, w2);
+                            if (COMPACT && hist4 && (u32)(h * 8 + t) < my_steps) __stcs(reinterpret_cast<uint2 *>(hist4) + (step0 + h * 8 + t) * 32 + lane, w2);
                             v[t] = make_uint4(w2.x & 0xFFFFu, w2.x >> 16, w2.y & 0xFFFFu, w2.y >> 16);
                         } else {
                             const uint2 c2 = *reinterpret_cast<const uint2 *>(sh + wb + t * 64),
@@ -1146,7 +1172,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                             v[t] = make_uint4(c2.x, u2.x, c2.y, u2.y);
                         }
                     }
-                    if (hist4 && !(PACKED && hist16)) {
+                    if (hist4 && !COMPACT) {
                         uint4 *dst = hist4 + (step0 + h * 8) * 32 + lane;
 #pragma unroll
                         for (int t = 0; t < 8; ++t) if ((u32)(h * 8 + t) < my_steps) __stcs(dst + t * 32, v[t]);
@@ -1213,10 +1239,15 @@ k_fine_accumulate_cluster(const u32 *__restrict__ fine, const u32 *__restrict__ 
         const u32 lo = __ldg(start + f), cnt = __ldg(start + f + 1) - lo;
         for (u32 k = tid; k < 2 * FINE_BINS / 4; k += NT) reinterpret_cast<uint4 *>(sh)[k] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        for (u32 i0 = r * TAKE; i0 < cnt; i0 += FINE_CL * TAKE) {
-            u32 v[8];
+        // my share of the items, eight per thread at a time; a batch is requested before the one before it is applied
+        u32 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = i0 + k * NT + tid < cnt ? __ldcs(fine + lo + i0 + k * NT + tid) : ITEM_SKIP;
+        for (int k = 0; k < 8; ++k) v[k] = r * TAKE + k * NT + tid < cnt ? __ldcs(fine + lo + r * TAKE + k * NT + tid) : ITEM_SKIP;
+        for (u32 i0 = r * TAKE; i0 < cnt; i0 += FINE_CL * TAKE) {
+            u32 nx[8];
+            const u32 i1 = i0 + FINE_CL * TAKE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nx[k] = i1 + k * NT + tid < cnt ? __ldcs(fine + lo + i1 + k * NT + tid) : ITEM_SKIP;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (v[k] != ITEM_SKIP) {
@@ -1224,6 +1255,8 @@ k_fine_accumulate_cluster(const u32 *__restrict__ fine, const u32 *__restrict__ 
                     atomicAdd(&sh[b], 1u);
                     if (v[k] >> 31) atomicAdd(&sh[FINE_BINS + b], 1u);
                 }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = nx[k];
         }
         cl.sync();                                             // every copy is complete
 #pragma unroll
@@ -1241,7 +1274,7 @@ k_fine_accumulate_cluster(const u32 *__restrict__ fine, const u32 *__restrict__ 
         const u64 step = (((u64)f << FINE_SHIFT) >> 6) + r * (SHARE / 64) + wid;      // my warp's 64 bins
         if (step < n_steps) {
             const u64 first_bin = step << 6;
-            u32 a = __ldg(fine_ref + f), b = min(__ldg(fine_ref + f + 1) + 1u, G);    // largest g in [a, b) with off[g] <= my first bin
+            u32 a = __ldg(fine_ref + first_bin / FINE_REF_BLOCK), b = min(__ldg(fine_ref + first_bin / FINE_REF_BLOCK + 1) + 1u, G);    // largest g in [a, b) with off[g] <= my first bin
             while (b - a > 1) { const u32 mid = (a + b) >> 1; if (__ldg(off + mid) <= first_bin) a = mid; else b = mid; }
             const u32 wb = r * SHARE + wid * 64 + 2 * lane;    // lane l holds bins 2l, 2l+1 of the step
             const uint2 c2 = *reinterpret_cast<const uint2 *>(sh + wb), u2 = *reinterpret_cast<const uint2 *>(sh + FINE_BINS + wb);

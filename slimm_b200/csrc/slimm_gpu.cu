@@ -190,18 +190,19 @@ static int layout_bins(slimm_gpu_ctx *ctx)
         if (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2) CU(cudaMalloc(&ctx->d_cov2, std::max<u64>(Bp, 64) * 4));
         ctx->Bp = Bp;
     }
-    {   // the reference that holds the first bin of every fine slice (k_fine_accumulate starts its segment walk there)
-        const u64 n_fine = (Bp + FINE_BINS - 1) >> FINE_SHIFT;
-        std::vector<u32> fr(n_fine + 1);
+    {   // the reference that holds the first bin of every block of FINE_REF_BLOCK bins: a warp of the accumulate kernels starts its segment
+        // walk there (one look-up instead of a binary search over the references of the slice)
+        const u64 n_blk = (Bp + FINE_REF_BLOCK - 1) / FINE_REF_BLOCK;
+        std::vector<u32> fr(n_blk + 1);
         u32 g = 0;
-        for (u64 f = 0; f <= n_fine; ++f) {
-            const u64 bin = std::min(f << FINE_SHIFT, Bp ? Bp - 1 : 0);
+        for (u64 k = 0; k <= n_blk; ++k) {
+            const u64 bin = std::min(k * FINE_REF_BLOCK, Bp ? Bp - 1 : 0);
             while (g + 1 < G && ctx->h_off[g + 1] <= bin) ++g;
-            fr[f] = g;
+            fr[k] = g;
         }
         cudaFree(ctx->d_fine_ref); ctx->d_fine_ref = nullptr;
-        CU(cudaMalloc(&ctx->d_fine_ref, (n_fine + 1) * 4));
-        CU(cudaMemcpy(ctx->d_fine_ref, fr.data(), (n_fine + 1) * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_fine_ref, (n_blk + 1) * 4));
+        CU(cudaMemcpy(ctx->d_fine_ref, fr.data(), (n_blk + 1) * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(ctx->d_meta, meta.data(), (size_t)G * sizeof(uint4), cudaMemcpyHostToDevice));
     {
@@ -279,9 +280,10 @@ int slimm_gpu_create(const slimm_gpu_config *cfg, slimm_gpu_ctx **out)
     CU(cudaMalloc(&ctx->d_cut_prefix, (size_t)cfg->n_refs * 8));
     if (const char *e = getenv("SLIMM_GPU_ACC")) ctx->acc_mode = !strcmp(e, "l2") ? 0 : 1;
     if ((ctx->flags & SLIMM_GPU_SKIP_BINS) && (ctx->flags & SLIMM_GPU_KEEP_UNIQ_COV2)) return fail(ctx, SLIMM_GPU_EINVAL, "SLIMM_GPU_SKIP_BINS and SLIMM_GPU_KEEP_UNIQ_COV2 exclude each other");
-    CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate<false, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
     CU(cudaFuncSetAttribute(k_fine_accumulate_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FINE_BINS * 4));
-    CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
+    CU(cudaFuncSetAttribute(k_fine_accumulate<true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_BINS * 4));
     if (const char *e = getenv("SLIMM_GPU_FINE")) ctx->fine_packed = strcmp(e, "wide") != 0;
     if (const char *e = getenv("SLIMM_GPU_FINE_CLUSTER")) ctx->fine_cluster = atoi(e) != 0;
     if (const char *e = getenv("SLIMM_GPU_COMPACT_BINS")) ctx->compact_bins = atoi(e) != 0;
@@ -501,8 +503,15 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     }
     k_fine_scan<<<FINE_SCAN_CL, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot, n_hot, vhot, n_vhot);
     if (n_tiles) {
-        const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
-        k_fine_split<<<sgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
+        static const int fnt = getenv("SLIMM_FINE_SPLIT_NT") ? atoi(getenv("SLIMM_FINE_SPLIT_NT")) : 256;   // tile shape (experiments)
+        if (fnt >= 512) {
+            const u64 tiles = (n_cap + 512 * FINE_ITEMS - 1) / (512 * FINE_ITEMS);
+            const int sgrid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ctx->sm_count * 2));
+            k_fine_split<512, FINE_ITEMS><<<sgrid, 512, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
+        } else {
+            const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
+            k_fine_split<256, FINE_ITEMS><<<sgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
+        }
     }
     const u64 f_lo = lo_bin >> FINE_SHIFT, f_hi = (std::min(hi_bin, ctx->Bp) + FINE_BINS - 1) >> FINE_SHIFT;
     if (f_hi > f_lo) {
@@ -523,13 +532,17 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
         if (ctx->fine_packed) {
             // slices with fewer than 65536 items (all but the hottest): packed counters, two CTAs per SM; then the rest, wide
             const unsigned grid2 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count * FINE_PACKED_CTAS);
-            k_fine_accumulate<true, 512><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                  ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr, hist16);
+            if (hist16)
+                k_fine_accumulate<true, 512, true><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                            ctx->G, ctx->d_fine_ref, ctx->d_stats, (uint4 *)hist16, ticket, 0u, 65536u, nullptr, nullptr);
+            else
+                k_fine_accumulate<true, 512, false><<<grid2, 512, FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                             ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 65536u, nullptr, nullptr);
             // the hot slices k_fine_scan listed: wide counters, one CTA per slice (list positions handed out by a ticket); the very hot
             // ones: a cluster of CTAs per slice
             const unsigned grid1 = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
-            k_fine_accumulate<false, 1024><<<grid1, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, hot_ticket, 65536u, 0xFFFFFFFFu, ctx->d_fine_hot, n_hot, nullptr);
+            k_fine_accumulate<false, 1024, false><<<grid1, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                     ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, hot_ticket, 65536u, 0xFFFFFFFFu, ctx->d_fine_hot, n_hot);
             ctx->launches++;
             if (vhot) {
                 const unsigned n_cl = std::max(1u, (unsigned)ctx->sm_count / FINE_CL - 2u);
@@ -539,8 +552,8 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
             }
         } else {
             const unsigned grid = (unsigned)std::min<u64>(f_hi - f_lo, (u64)ctx->sm_count);
-            k_fine_accumulate<false, 1024><<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
-                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu, nullptr, nullptr, nullptr);
+            k_fine_accumulate<false, 1024, false><<<grid, 1024, 2 * FINE_BINS * 4, ctx->stream>>>(out_buf, ctx->d_fine_start, (u32)f_lo, (u32)f_hi, ctx->Bp, ctx->d_off,
+                                                                                    ctx->G, ctx->d_fine_ref, ctx->d_stats, hist4, ticket, 0u, 0xFFFFFFFFu, nullptr, nullptr);
         }
     }
     ctx->launches += 4;
