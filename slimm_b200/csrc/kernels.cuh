@@ -794,6 +794,72 @@ k_route(const u32 *__restrict__ items, u32 n, u32 shift, u32 n_ranks, RoutePlan 
     }
 }
 
+// ---- block exchange (sharded runs; SLIMM_PEER_ROUTE=2) ------------------------------------------------------------------
+// Routed, every item is ranked twice (by owner rank before it travels, by slice after) and the sender's ranking pass runs at
+// link speed at best.  Here the sender groups its items by slice exactly as a single GPU does (k_split into local memory, HBM
+// speed); a rank owns CONSECUTIVE slices, so its share of the grouped items is one contiguous block, and k_peer_copy streams
+// the n blocks to their owners (128-byte-aligned stores over NVLink, all links at once).  The receiver holds the blocks source
+// by source, each ordered by slice - what k_fine_count / k_fine_split need (a tile spans one or two coarse slices; the few
+// tiles across two blocks go through their overflow paths) - so there is no second coarse pass at all.
+struct CopyPlan {
+    u32 *dst[ROUTE_MAX_RANKS];       // where THIS rank's block for rank q starts inside q's receive buffer
+    u32 src_off[ROUTE_MAX_RANKS];    // where the block starts inside this rank's grouped items
+    u32 len[ROUTE_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(MAX_BUCKETS)
+k_peer_copy_plan(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32 n_slices, u32 n_ranks, u32 me, u32 *const *__restrict__ peer_recv,
+                 u64 recv_cap, CopyPlan *__restrict__ plan, u32 *__restrict__ n_recv, u32 *__restrict__ overflow)
+{
+    __shared__ u32 s_from[ROUTE_MAX_RANKS][ROUTE_MAX_RANKS];       // [q][src]: items src sends to q
+    const u32 tid = threadIdx.x;
+    u32 q_of = 0;                                                  // owner of slice tid: slices [ns q / n, ns (q+1) / n)
+    if (tid < n_slices) while ((u64)n_slices * (q_of + 1) / n_ranks <= tid) ++q_of;
+    for (u32 i = tid; i < ROUTE_MAX_RANKS * ROUTE_MAX_RANKS; i += MAX_BUCKETS) (&s_from[0][0])[i] = 0;
+    __syncthreads();
+    if (tid < n_slices)
+        for (u32 src = 0; src < n_ranks; ++src) {
+            const u32 c = all_counts[(size_t)src * n_slices + tid];
+            if (c) atomicAdd(&s_from[q_of][src], c);
+        }
+    __syncthreads();
+    if (tid < n_ranks) {
+        u32 before = 0, all = 0, off = 0;
+        for (u32 src = 0; src < n_ranks; ++src) { if (src < me) before += s_from[tid][src]; all += s_from[tid][src]; }
+        for (u32 q = 0; q < tid; ++q) off += s_from[q][me];
+        plan->dst[tid] = peer_recv[tid] + before;
+        plan->src_off[tid] = off;
+        plan->len[tid] = s_from[tid][me];
+        if ((u64)all > recv_cap) atomicOr(overflow, 1u);
+        if (tid == me) *n_recv = all;
+    }
+}
+
+#define PCOPY_CHUNK 8192u
+__global__ void __launch_bounds__(256)
+k_peer_copy(const u32 *__restrict__ grouped, const CopyPlan *__restrict__ plan, u32 n_ranks, u32 me)
+{
+    const u32 tid = threadIdx.x;
+    for (u32 k = 0; k < n_ranks; ++k) {
+        const u32 q = (me + 1 + k + blockIdx.x) % n_ranks;         // CTAs start on different links
+        u32 *__restrict__ dst = plan->dst[q];
+        const u32 *__restrict__ src = grouped + plan->src_off[q];
+        const u32 len = plan->len[q];
+        // chunks are cut where the DESTINATION is 128-byte aligned: whole lines over the link
+        const u32 head = min(len, (32u - (u32)((reinterpret_cast<uintptr_t>(dst) >> 2) & 31u)) & 31u);
+        if (blockIdx.x == 0 && tid < head) dst[tid] = src[tid];
+        const u32 body = len - head, n_chunks = (body + PCOPY_CHUNK - 1) / PCOPY_CHUNK;
+        for (u32 c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+            const u32 o = head + c * PCOPY_CHUNK, m = min(PCOPY_CHUNK, len - o);
+            u32 v[PCOPY_CHUNK / 256];
+#pragma unroll
+            for (u32 j = 0; j < PCOPY_CHUNK / 256; ++j) if (j * 256 + tid < m) v[j] = __ldcs(src + o + j * 256 + tid);
+#pragma unroll
+            for (u32 j = 0; j < PCOPY_CHUNK / 256; ++j) if (j * 256 + tid < m) dst[o + j * 256 + tid] = v[j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 accumulate: applies the grouped items in stream order, one 64-bit RED each: the CTAs in flight work
 // on one or two adjacent histogram slices, so the REDs meet in L2 and a slice's sectors travel HBM -> L2 ->

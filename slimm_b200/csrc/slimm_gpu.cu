@@ -84,7 +84,8 @@ struct slimm_gpu_ctx {
     u32 *d_recv = nullptr; u64 recv_cap = 0, n_recv = 0; std::vector<u32 *> peer_recv; bool p2p = false, split_pending = false;
     u32 **d_dest = nullptr; u32 **d_peer_recv = nullptr; u32 *d_n_recv = nullptr;   // d_n_recv[0]: items this rank receives, [1]: a receive buffer would overflow
     // routed exchange: a tile's share of a RANK travels as one segment, the receiver groups by slice (k_route, k_peer_route_plan)
-    RoutePlan *d_route = nullptr; Sched *d_sched2 = nullptr; u32 *d_recv2 = nullptr; u64 recv2_cap = 0; bool routed = false; int route_mode = 1;
+    RoutePlan *d_route = nullptr; Sched *d_sched2 = nullptr; u32 *d_recv2 = nullptr; u64 recv2_cap = 0; bool routed = false; int route_mode = 2;   // 0: k_split<PEER> stores runs per slice, 1: k_route + receiver-side k_split, 2: local k_split + k_peer_copy of the owners' blocks
+    CopyPlan *d_copy_plan = nullptr;
     bool n_recv_on_device = false;          // the split was planned on the device (slimm_gpu_split_to_peers_device): n_recv lives there
     // slimm_gpu_push_packed: staging of the wire format + the running read-id counter
     u32 *d_pk_bits = nullptr; unsigned short *d_pk_ref16 = nullptr; u32 *d_pk_tiles = nullptr, *d_pk_counter = nullptr; u64 pk_cap = 0;
@@ -334,7 +335,7 @@ int slimm_gpu_destroy(slimm_gpu_ctx *ctx)
     cudaFree(ctx->d_valid_bytes); cudaFree(ctx->d_assign); cudaFree(ctx->d_sc); cudaFree(ctx->d_tmp_bins);
     cudaFree(ctx->d_items); cudaFree(ctx->d_grouped); cudaFree(ctx->d_sched); cudaFree(ctx->d_lvl_idx); cudaFree(ctx->d_top_lvl7); cudaFree(ctx->d_agg); if (ctx->h_agg) cudaFreeHost(ctx->h_agg); if (ctx->h_sc) cudaFreeHost(ctx->h_sc); cudaFree(ctx->d_cw); cudaFree(ctx->d_cw_idx); cudaFree(ctx->d_lr); cudaFree(ctx->d_chunk_cnt);
     cudaFree(ctx->d_rs); cudaFree(ctx->d_lin16); cudaFree(ctx->d_lin16v); cudaFree(ctx->d_dest); cudaFree(ctx->d_peer_recv); cudaFree(ctx->d_n_recv);
-    cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref); cudaFree(ctx->d_fine_hot);
+    cudaFree(ctx->d_fine_cnt); cudaFree(ctx->d_fine_start); cudaFree(ctx->d_fine_cursor); cudaFree(ctx->d_fine); cudaFree(ctx->d_fine_ref); cudaFree(ctx->d_fine_hot); cudaFree(ctx->d_copy_plan);
     for (u32 q = 0; q < ctx->peer_recv.size(); ++q) if (ctx->peer_recv[q] && q != ctx->shard_rank) cudaIpcCloseMemHandle(ctx->peer_recv[q]);
     cudaFree(ctx->d_recv);
     cudaFree(ctx->d_rid_sorted); cudaFree(ctx->d_rp_sorted); cudaFree(ctx->d_kind); cudaFree(ctx->d_val);
@@ -990,7 +991,8 @@ int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles, uint32_t 
     if (!ctx->d_dest) CU(cudaMalloc(&ctx->d_dest, MAX_BUCKETS * sizeof(u32 *)));
     if (!ctx->d_n_recv) CU(cudaMalloc(&ctx->d_n_recv, 8));
     if (!ctx->d_route) { CU(cudaMalloc(&ctx->d_route, sizeof(RoutePlan))); CU(cudaMalloc(&ctx->d_sched2, sizeof(Sched))); }
-    if (const char *e = getenv("SLIMM_PEER_ROUTE")) ctx->route_mode = atoi(e) != 0;
+    if (const char *e = getenv("SLIMM_PEER_ROUTE")) ctx->route_mode = std::max(0, std::min(2, atoi(e)));
+    if (!ctx->d_copy_plan) CU(cudaMalloc(&ctx->d_copy_plan, sizeof(CopyPlan)));
     cudaFree(ctx->d_peer_recv); ctx->d_peer_recv = nullptr;
     CU(cudaMalloc(&ctx->d_peer_recv, n_ranks * sizeof(u32 *)));
     CU(cudaMemcpy(ctx->d_peer_recv, ctx->peer_recv.data(), n_ranks * sizeof(u32 *), cudaMemcpyHostToDevice));
@@ -1053,6 +1055,26 @@ int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_co
     TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);
     CU(cudaMemsetAsync(ctx->d_n_recv, 0, 8, ctx->stream));
     ctx->routed = ctx->route_mode == 1 && ctx->shard_n <= ROUTE_MAX_RANKS && ctx->acc_mode == 1;
+    const bool blocks = ctx->route_mode == 2 && ctx->shard_n <= ROUTE_MAX_RANKS && ctx->acc_mode == 1;
+    if (blocks) {
+        // group by slice locally (as one GPU does), then every owner's block travels as one contiguous copy
+        k_peer_copy_plan<<<1, MAX_BUCKETS, 0, ctx->stream>>>(d_all_counts, ns, ctx->shard_n, ctx->shard_rank, ctx->d_peer_recv, ctx->recv_cap, ctx->d_copy_plan,
+                                                             ctx->d_n_recv, ctx->d_n_recv + 1);
+        ctx->launches++;
+        ctx->n_recv_on_device = true;
+        ctx->n_recv = ctx->recv_cap;
+        if (ctx->split_pending) {
+            const u32 n = (u32)ctx->n;
+            launch_k_split<false>(ctx, 0, ctx->d_items, n, ctx->bucket_shift, ns, ctx->d_grouped, nullptr);
+            const u64 chunks = ((u64)n + PCOPY_CHUNK - 1) / PCOPY_CHUNK + ctx->shard_n;
+            const int grid = (int)std::max<u64>(1, std::min<u64>(chunks, (u64)ctx->sm_count * 4));
+            k_peer_copy<<<grid, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_copy_plan, ctx->shard_n, ctx->shard_rank);
+            ctx->launches += 2;
+            ctx->split_pending = false;
+        }
+        CU(cudaGetLastError());
+        return SLIMM_GPU_OK;
+    }
     if (ctx->routed) {
         if (ctx->recv2_cap < ctx->recv_cap) {
             cudaFree(ctx->d_recv2); ctx->d_recv2 = nullptr; ctx->recv2_cap = 0;

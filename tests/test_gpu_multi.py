@@ -27,7 +27,13 @@ def _case(w):
     return contigs, rec, lineage, {t: v for t, v in db.taxid__name.items()}
 
 
-def _worker(rank, world, port, w, p2p, out):
+_PEER_MODES = {"p2p_split": "0", "p2p_route": "1", "p2p_blocks": "2"}   # SLIMM_PEER_ROUTE (csrc/slimm_gpu.cu)
+
+
+def _worker(rank, world, port, w, exchange, out):
+    p2p = exchange in _PEER_MODES
+    if p2p:
+        os.environ["SLIMM_PEER_ROUTE"] = _PEER_MODES[exchange]
     import torch
     import torch.distributed as dist
     from slimm_b200 import dist as sdist
@@ -96,9 +102,12 @@ def _worker(rank, world, port, w, p2p, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True], ids=["nccl_all_to_all", "p2p_split"])
+@pytest.mark.parametrize("exchange", ["nccl_all_to_all", "p2p_split", "p2p_route", "p2p_blocks"])
 @pytest.mark.parametrize("w", [10, 1000])
-def test_two_gpus_match_oracle(w, p2p):
+def test_two_gpus_match_oracle(w, exchange):
+    """The four item exchanges: one NCCL all-to-all of the slice-grouped items; peer stores inside the split (runs per slice);
+    routed (ranked by owner, grouped by slice on arrival); blocks (grouped by slice locally, one contiguous copy per owner - the
+    default)."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -106,7 +115,7 @@ def test_two_gpus_match_oracle(w, p2p):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, w, p2p, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, w, exchange, out)) for r in range(2)]
     for p in procs:
         p.start()
     results = [out.get(timeout=600) for _ in procs]
