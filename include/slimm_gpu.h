@@ -123,8 +123,10 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx);
  * (read, ref), scatter-add into the cov / uniq_cov bins.  Leaves THIS rank's partial histogram on
  * the device; with several GPUs sum slimm_gpu_bins_device() across ranks before stage 2. */
 int slimm_gpu_coverage(slimm_gpu_ctx *ctx);
-/* Device pointer to the interleaved {cov, uniq_cov} u32 histogram (2*n_words_per... see DESIGN.md)
- * for an in-place NCCL sum; n_u32 is the number of u32 words. */
+/* Device pointer to the interleaved {cov, uniq_cov} u32 histogram for an in-place sum over ranks;
+ * n_u32 is the number of u32 words.  Only for runs that keep the interleaved layout (small histograms, SLIMM_GPU_ACC=l2,
+ * SLIMM_GPU_COMPACT_BINS=0): the fine-slice accumulate keeps most bins as {cov:16 | uniq_cov:16} words and answers
+ * SLIMM_GPU_ESTATE here - read bins with slimm_gpu_fetch_bins. */
 int slimm_gpu_bins_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
 /* Device pointer to the read-level partial counters {matches_count, uniq_matches_count} (2 x u64,
  * summed across ranks together with the bins). */
@@ -159,8 +161,12 @@ int slimm_gpu_stats_device(slimm_gpu_ctx *ctx, void **d_ptr, uint64_t *n_u32);
  *   per sample: slimm_gpu_coverage (stops before the split); all-gather slimm_gpu_get_slice_counts over ranks;
  *              slimm_gpu_split_to_peers(table [n_ranks][n_slices]); a cross-rank barrier ordered on the stream (all
  *              splits complete); slimm_gpu_accumulate_received; then as above (sum the statistics, filter, ...).
- * Inside a receive buffer the items lie slice by slice (sources in rank order inside a slice), so the owner's
- * accumulate walks one L2-resident slice after the other exactly as in the single-GPU path. */
+ * Three exchanges behind the same calls (SLIMM_PEER_ROUTE, read by slimm_gpu_p2p_connect):
+ *   2 (default) blocks: the items are grouped by slice locally, as on one GPU; a rank owns consecutive slices, so its share is one
+ *               contiguous block, copied to its receive buffer with 128-byte-aligned stores over NVLink (k_peer_copy).  The
+ *               receiver holds the blocks source by source, each ordered by slice, and needs no coarse pass of its own.
+ *   1 routed:   a tile's items are ranked by owner rank and travel as one segment per (tile, rank); the receiver groups by slice.
+ *   0 split:    the multisplit stores every (tile, slice) run straight into the owner's buffer (runs of ~20 items). */
 int slimm_gpu_p2p_reserve(slimm_gpu_ctx *ctx, uint64_t cap_items, void *ipc_handle_64);
 int slimm_gpu_p2p_connect(slimm_gpu_ctx *ctx, const void *ipc_handles /* [n_ranks][64] */, uint32_t n_ranks);
 int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts /* [n_ranks][n_slices] */, uint64_t *n_recv);

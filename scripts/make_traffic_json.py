@@ -9,7 +9,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GROUP = {"k_coverage": "coverage", "k_accumulate": "accumulate", "k_ref_stats": "stats", "k_assign": "assign", "k_split": "split",
+GROUP = {"k_coverage": "coverage", "k_coverage_tile": "coverage", "k_fine_accumulate_cluster": "accumulate", "k_split_bulk": "split", "k_accumulate": "accumulate", "k_ref_stats": "stats", "k_assign": "assign", "k_split": "split",
          "k_cutoffs_cluster": "cutoff", "k_cutoffs": "cutoff", "k_assign_reads": "assign", "k_fine_count": "accumulate",
          "k_fine_scan": "accumulate", "k_fine_split": "accumulate", "k_fine_accumulate": "accumulate"}
 RECORDS = {"cfg2": 10_000_000, "cfg3": 100_000_000, "cfg4": 100_000_000, "cfg5": 1_000_000_000}
@@ -28,9 +28,15 @@ for spec in sys.argv[2:]:
             continue
         d = per.setdefault(r[0], {"kernel": k, "bytes": 0.0})
         d["bytes"] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
+    # one hot-path step = the launches from one coverage kernel to the next; the last COMPLETE step counts, every launch of it
+    # (k_fine_accumulate runs three times per step: packed, wide, cluster)
+    order = [d for _, d in sorted(per.items(), key=lambda x: int(x[0]))]
+    starts = [i for i, d in enumerate(order) if GROUP[d["kernel"]] == "coverage"]
+    if len(starts) >= 2:
+        order = order[starts[-2]:starts[-1]]
     last = {}
-    for _, d in sorted(per.items(), key=lambda x: int(x[0])):       # later launches overwrite earlier ones, kernel by kernel
-        last[d["kernel"]] = d["bytes"]
+    for d in order:
+        last[d["kernel"]] = last.get(d["kernel"], 0.0) + d["bytes"]
     res = {}
     for k, b in last.items():                                       # a group is the sum of its kernels (one launch each per step)
         g = res.setdefault(GROUP[k], {"kernel": [], "dram_bytes_per_launch": 0.0})

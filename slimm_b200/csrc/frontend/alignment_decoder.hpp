@@ -25,6 +25,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "bytesource.hpp"
 #include "pipeline.hpp"
@@ -37,22 +40,20 @@ static inline uint64_t mum(uint64_t a, uint64_t b)
     const __uint128_t r = (__uint128_t)a * b;
     return (uint64_t)r ^ (uint64_t)(r >> 64);
 }
-static inline uint64_t load_tail(const char *p, size_t n)   // n < 8
-{
-    uint64_t v = 0;
-    memcpy(&v, p, n);
-    return v;
-}
+static inline uint64_t rd64u(const char *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline uint64_t rd32u(const char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+// fixed-size loads only (no variable-length memcpy): whole 8-byte words, then the LAST eight bytes once more (they overlap the
+// words before when the length is not a multiple of 8); fewer than 8 bytes: two overlapping 4-byte loads or three single bytes
 static inline uint64_t hash_bytes(const char *p, size_t n)
 {
     uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xD6E8FEB86659FD93ull);
-    while (n >= 8) {
-        uint64_t v;
-        memcpy(&v, p, 8);
-        h = mum(h ^ v, 0xA0761D6478BD642Full);
-        p += 8; n -= 8;
-    }
-    h = mum(h ^ load_tail(p, n), 0xE7037ED1A0B428DBull);
+    if (n >= 8) {
+        const char *last = p + n - 8;
+        for (; p < last; p += 8) h = mum(h ^ rd64u(p), 0xA0761D6478BD642Full);
+        h = mum(h ^ rd64u(last), 0xE7037ED1A0B428DBull);
+    } else if (n >= 4) h = mum(h ^ (rd32u(p) | (rd32u(p + n - 4) << 32)), 0xE7037ED1A0B428DBull);
+    else if (n) h = mum(h ^ ((uint64_t)(unsigned char)p[0] | ((uint64_t)(unsigned char)p[n >> 1] << 8) | ((uint64_t)(unsigned char)p[n - 1] << 16)), 0xE7037ED1A0B428DBull);
+    else h = mum(h, 0xE7037ED1A0B428DBull);
     return h ^ (h >> 29);
 }
 
@@ -62,7 +63,9 @@ struct AlignmentHeader {
     std::vector<uint32_t> lengths;    // @SQ LN / l_ref
 };
 
-// open-addressing map contig name -> index (RNAME lookup of the SAM text parser)
+// open-addressing map contig name -> index (RNAME lookup of the SAM text parser).  A slot is 32 bytes and holds the name
+// itself when it is at most 23 bytes long (accessions are), so a look-up touches ONE cache line of a table that does not fit
+// the L2 of a core (50 000 contigs: 4 MB) instead of three dependent ones (slot -> std::string -> characters).
 class NameIndex {
 public:
     void build(const std::vector<std::string> &names)
@@ -70,59 +73,93 @@ public:
         names_ = &names;
         size_t cap = 16;
         while (cap < names.size() * 2 + 2) cap <<= 1;
-        slot_.assign(cap, -1);
+        slot_.assign(cap, Slot{});
         mask_ = cap - 1;
         for (size_t i = 0; i < names.size(); ++i) {
-            size_t s = hash_bytes(names[i].data(), names[i].size()) & mask_;
-            while (slot_[s] >= 0) {
-                if ((*names_)[slot_[s]] == names[i]) break;   // duplicate @SQ: SeqAn's name cache resolves to the first
+            const uint64_t h = hash_bytes(names[i].data(), names[i].size());
+            size_t s = h & mask_;
+            bool dup = false;
+            while (slot_[s].idx1) {
+                if ((*names_)[slot_[s].idx1 - 1] == names[i]) { dup = true; break; }   // duplicate @SQ: SeqAn's name cache resolves to the first
                 s = (s + 1) & mask_;
             }
-            if (slot_[s] < 0) slot_[s] = (int32_t)i;
+            if (dup) continue;
+            Slot &sl = slot_[s];
+            sl.idx1 = (uint32_t)i + 1;
+            sl.tag = (uint32_t)(h >> 32);
+            sl.len = names[i].size() <= INLINE ? (uint8_t)names[i].size() : (uint8_t)0xFF;
+            if (names[i].size() <= INLINE) memcpy(sl.name, names[i].data(), names[i].size());
         }
     }
-    int32_t find(const char *p, size_t n) const
+    void prefetch(uint64_t h) const { __builtin_prefetch(&slot_[h & mask_]); }
+    int32_t find(const char *p, size_t n) const { return find(hash_bytes(p, n), p, n); }
+    int32_t find(uint64_t h, const char *p, size_t n) const      // h = hash_bytes(p, n)
     {
-        size_t s = hash_bytes(p, n) & mask_;
-        while (slot_[s] >= 0) {
-            const std::string &nm = (*names_)[slot_[s]];
-            if (nm.size() == n && memcmp(nm.data(), p, n) == 0) return slot_[s];
+        const uint32_t tag = (uint32_t)(h >> 32);
+        size_t s = h & mask_;
+        while (slot_[s].idx1) {
+            const Slot &sl = slot_[s];
+            if (sl.tag == tag) {
+                if (sl.len != 0xFF) { if (sl.len == n && memcmp(sl.name, p, n) == 0) return (int32_t)(sl.idx1 - 1); }
+                else {
+                    const std::string &nm = (*names_)[sl.idx1 - 1];
+                    if (nm.size() == n && memcmp(nm.data(), p, n) == 0) return (int32_t)(sl.idx1 - 1);
+                }
+            }
             s = (s + 1) & mask_;
         }
         return -1;
     }
 
 private:
+    static const size_t INLINE = 23;
+    struct alignas(32) Slot { uint32_t idx1 = 0, tag = 0; uint8_t len = 0; char name[INLINE] = {}; };
+    static_assert(sizeof(Slot) == 32, "one slot, half a cache line");
     const std::vector<std::string> *names_ = nullptr;
-    std::vector<int32_t> slot_;
+    std::vector<Slot> slot_;
     size_t mask_ = 0;
 };
 
 // ---- one parsed chunk ---------------------------------------------------------------------------
 struct ParsedChunk {
+    // arrays sized ahead of the records (ensure()), n of them in use: a record costs six plain stores, not six push_backs
     std::vector<uint64_t> hash;
     std::vector<uint32_t> key_off, key_len, ref;
     std::vector<int32_t> pos;
-    std::vector<char> keys;          // read keys back to back
+    std::vector<char> keys;          // read keys back to back (keys_used bytes)
     std::vector<uint8_t> new_run;    // grouped-input fast path: record i >= 1 starts another read than record i - 1
+    std::vector<uint64_t> heads, scratch;   // grouped-input fast path: the chunk's run-head hashes (kept here so that a recycled chunk brings its buffers)
+    size_t n = 0, keys_used = 0;
     uint64_t n_records = 0;          // records seen, kept or not
     std::string error;
-    void clear() { hash.clear(); key_off.clear(); key_len.clear(); ref.clear(); pos.clear(); keys.clear(); new_run.clear(); n_records = 0; error.clear(); }
+    void clear() { n = 0; keys_used = 0; new_run.clear(); n_records = 0; error.clear(); }
+    void ensure(size_t records)
+    {
+        if (hash.size() < records) { hash.resize(records); key_off.resize(records); key_len.resize(records); ref.resize(records); pos.resize(records); }
+        if (keys.size() < records * 24) keys.resize(records * 24);
+    }
     bool same_key(size_t i, size_t j) const
     {
         return hash[i] == hash[j] && key_len[i] == key_len[j] && memcmp(keys.data() + key_off[i], keys.data() + key_off[j], key_len[i]) == 0;
     }
-    size_t size() const { return hash.size(); }
-    void add(const char *name, size_t name_len, uint32_t flag, uint32_t rid, int32_t begin_pos)
+    size_t size() const { return n; }
+    // readable_end (optional): bytes up to there may be read (the rest of the record): short names are copied as two fixed
+    // 16-byte moves instead of a variable-length memcpy call
+    void add(const char *name, size_t name_len, uint32_t flag, uint32_t rid, int32_t begin_pos, const char *readable_end = nullptr)
     {
-        const size_t off = keys.size();
-        keys.insert(keys.end(), name, name + name_len);
-        if (flag & 0x40u) { keys.push_back('.'); keys.push_back('1'); }        // reference src/slimm.hpp:205-208
-        else if (flag & 0x80u) { keys.push_back('.'); keys.push_back('2'); }
-        const size_t len = keys.size() - off;
-        key_off.push_back((uint32_t)off); key_len.push_back((uint32_t)len);
-        hash.push_back(hash_bytes(keys.data() + off, len));
-        ref.push_back(rid); pos.push_back(begin_pos);
+        if (n == hash.size()) ensure(std::max<size_t>(1024, n * 2));
+        if (keys_used + name_len + 34 > keys.size()) keys.resize(std::max(keys.size() * 2, keys_used + name_len + 34 + 4096));
+        char *k = keys.data() + keys_used;
+        if (name_len <= 32 && readable_end && name + 32 <= readable_end) { memcpy(k, name, 16); memcpy(k + 16, name + 16, 16); }
+        else memcpy(k, name, name_len);
+        size_t len = name_len;
+        if (flag & 0x40u) { k[len++] = '.'; k[len++] = '1'; }               // reference src/slimm.hpp:205-208
+        else if (flag & 0x80u) { k[len++] = '.'; k[len++] = '2'; }
+        key_off[n] = (uint32_t)keys_used; key_len[n] = (uint32_t)len;
+        hash[n] = hash_bytes(k, len);
+        ref[n] = rid; pos[n] = begin_pos;
+        ++n;
+        keys_used += len;
     }
 };
 
@@ -137,11 +174,34 @@ static inline bool parse_u32(const char *p, const char *e, uint32_t &out)
 {
     if (p == e) return false;
     uint64_t v = 0;
-    for (; p < e; ++p) {
-        if (*p < '0' || *p > '9') return false;
-        v = v * 10 + (uint64_t)(*p - '0');
-        if (v > 0xFFFFFFFFull) return false;
-    }
+    if (e - p <= 9) {                                            // cannot overflow: one range test per digit is all
+        for (; p < e; ++p) {
+            const unsigned d = (unsigned)(unsigned char)*p - '0';
+            if (d > 9) return false;
+            v = v * 10 + d;
+        }
+    } else
+        for (; p < e; ++p) {
+            if (*p < '0' || *p > '9') return false;
+            v = v * 10 + (uint64_t)(*p - '0');
+            if (v > 0xFFFFFFFFull) return false;
+        }
+    out = (uint32_t)v;
+    return true;
+}
+
+// The same for a field of at most eight characters when the eight bytes that END at e may be read (lo = start of the record):
+// one 8-byte load, the bytes before the field replaced by '0', all digits tested and combined at once.
+static inline bool parse_u32_swar(const char *p, const char *e, const char *lo, uint32_t &out)
+{
+    const size_t n = (size_t)(e - p);
+    if (n == 0 || n > 8 || e - 8 < lo) return parse_u32(p, e, out);
+    uint64_t v = rd64u(e - 8);                                  // first character of the field in the lowest of its bytes
+    if (n < 8) v = (v >> (8 * (8 - n)) << (8 * (8 - n))) | (0x3030303030303030ull >> (8 * n));
+    v -= 0x3030303030303030ull;
+    if ((v | (v + 0x7676767676767676ull)) & 0x8080808080808080ull) return false;    // a byte above 9 (or below '0': it wrapped)
+    v = v * 10 + (v >> 8);
+    v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
     out = (uint32_t)v;
     return true;
 }
@@ -153,13 +213,24 @@ static inline bool parse_sam_line(const char *p, const char *e, const NameIndex 
     if (p == e) return true;                                    // blank line
     if (*p == '@') return true;                                 // header line
     ++out.n_records;
-    const char *t1 = (const char *)memchr(p, '\t', e - p);
-    if (!t1) { out.error = "SAM record with fewer than 4 fields"; return false; }
-    const char *t2 = (const char *)memchr(t1 + 1, '\t', e - t1 - 1);
-    if (!t2) { out.error = "SAM record with fewer than 4 fields"; return false; }
-    const char *t3 = (const char *)memchr(t2 + 1, '\t', e - t2 - 1);
+    // the first four tabs: QNAME, FLAG, RNAME and POS end within the first few dozen bytes, one or two 16-byte compares find them
+    const char *tabs[4] = {nullptr, nullptr, nullptr, nullptr};
+    int nt = 0;
+    const char *q = p;
+#if defined(__SSE2__)
+    const __m128i tab = _mm_set1_epi8('\t');
+    while (nt < 4 && q + 16 <= e) {
+        unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(q)), tab));
+        while (m && nt < 4) { tabs[nt++] = q + __builtin_ctz(m); m &= m - 1; }
+        q += 16;
+    }
+#endif
+    if (nt < 4) {
+        if (nt) q = std::max(q, tabs[nt - 1] + 1);              // (the vector loop may have stopped short of e)
+        for (; q < e && nt < 4; ++q) if (*q == '\t') tabs[nt++] = q;
+    }
+    const char *t1 = tabs[0], *t2 = tabs[1], *t3 = tabs[2], *t4 = tabs[3];
     if (!t3) { out.error = "SAM record with fewer than 4 fields"; return false; }
-    const char *t4 = (const char *)memchr(t3 + 1, '\t', e - t3 - 1);
     if (!t4) t4 = e;
     uint32_t flag = 0, pos1 = 0;
     if (!parse_u32(t1 + 1, t2, flag) || flag > 0xFFFFu) { out.error = "SAM FLAG is not a 16-bit number"; return false; }
@@ -184,13 +255,59 @@ static inline bool parse_sam_line(const char *p, const char *e, const NameIndex 
     return true;
 }
 
+// The chunk parser of the decode pipeline: the same records as parse_sam_line line by line, but eight lines at a time - their
+// fields are located and the RNAME slots of the contig index requested first, the look-ups (one cache line each in a table
+// that does not fit a core's L2) and the stores follow when the lines have arrived.
 static inline void parse_sam_range(const char *p, const char *e, const NameIndex &idx, ParsedChunk &out)
 {
+    struct Line { const char *p, *e, *t1, *t2, *t3, *t4; uint64_t h; };
+    constexpr int B = 8;
+    Line L[B];
+#if defined(__SSE2__)
+    const __m128i tab = _mm_set1_epi8('\t');
+#endif
     while (p < e) {
-        const char *nl = (const char *)memchr(p, '\n', e - p);
-        const char *le = nl ? nl : e;
-        if (!parse_sam_line(p, le, idx, out, nullptr)) return;
-        p = le + 1;
+        int k = 0;
+        while (k < B && p < e) {
+            const char *nl = (const char *)memchr(p, '\n', e - p);
+            const char *le = nl ? nl : e, *next = le + 1;
+            if (le > p && le[-1] == '\r') --le;
+            if (p == le || *p == '@') { p = next; continue; }     // blank line, header line
+            Line &l = L[k];
+            l.p = p; l.e = le;
+            const char *tabs[4] = {nullptr, nullptr, nullptr, nullptr};
+            int nt = 0;
+            const char *q = p;
+#if defined(__SSE2__)
+            while (nt < 4 && q + 16 <= le) {
+                unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(q)), tab));
+                while (m && nt < 4) { tabs[nt++] = q + __builtin_ctz(m); m &= m - 1; }
+                q += 16;
+            }
+#endif
+            if (nt < 4) {
+                if (nt) q = std::max(q, tabs[nt - 1] + 1);
+                for (; q < le && nt < 4; ++q) if (*q == '\t') tabs[nt++] = q;
+            }
+            l.t1 = tabs[0]; l.t2 = tabs[1]; l.t3 = tabs[2]; l.t4 = tabs[3] ? tabs[3] : le;
+            if (l.t3) { l.h = hash_bytes(l.t2 + 1, (size_t)(l.t3 - l.t2 - 1)); idx.prefetch(l.h); }
+            ++k;
+            p = next;
+        }
+        for (int i = 0; i < k; ++i) {
+            const Line &l = L[i];
+            ++out.n_records;
+            if (!l.t3) { out.error = "SAM record with fewer than 4 fields"; return; }
+            uint32_t flag = 0, pos1 = 0;
+            if (!parse_u32(l.t1 + 1, l.t2, flag) || flag > 0xFFFFu) { out.error = "SAM FLAG is not a 16-bit number"; return; }
+            if (!parse_u32_swar(l.t3 + 1, l.t4, l.p, pos1)) { out.error = "SAM POS is not a number"; return; }
+            const char *rn = l.t2 + 1;
+            const size_t rn_len = (size_t)(l.t3 - rn);
+            if ((flag & 4u) || (rn_len == 1 && *rn == '*')) continue;   // reference src/slimm.hpp:197-198
+            const int32_t rid = idx.find(l.h, rn, rn_len);
+            if (rid < 0) { out.error = "SAM record names a reference that is not in the header: " + std::string(rn, rn_len); return; }
+            out.add(l.p, (size_t)(l.t1 - l.p), flag, (uint32_t)rid, (int32_t)pos1 - 1, l.e);
+        }
     }
 }
 
@@ -296,6 +413,17 @@ private:
 class RunHeadSet {
 public:
     RunHeadSet() : shards_(N_SHARDS) {}
+    // expected number of run heads (reads), e.g. from the size of the file: the shard tables start large enough that they are
+    // never rehashed (a rehash re-inserts every hash of the shard: cache misses all of them)
+    void reserve(uint64_t expected)
+    {
+        size_t cap = 1u << 10;
+        while (cap < expected / N_SHARDS * 2 + 16 && cap < (1u << 26)) cap <<= 1;
+        for (Shard &sh : shards_) {
+            std::lock_guard<std::mutex> lk(sh.m);
+            if (sh.slots.size() < cap && sh.n == 0) { sh.slots.assign(cap, 0); publish(sh); }
+        }
+    }
     // true when h was already there
     bool insert(uint64_t h)
     {
@@ -304,8 +432,10 @@ public:
         std::lock_guard<std::mutex> lk(sh.m);
         return insert_locked(sh, h);
     }
-    // A chunk's run heads at once: grouped by shard first, so that a shard is locked once per chunk and its small table
-    // stays in cache while the chunk's share goes in.  true when any of them was already there (or occurs twice here).
+    // A chunk's run heads at once: grouped by shard first, so that a shard is locked once per chunk.  The tables together are far
+    // larger than any cache (16 bytes per read), so every insert is a miss: the slots of the shards LOOKAHEAD places further on
+    // are requested while this shard's share goes in, which overlaps the misses instead of paying them one after the other.
+    // true when any of the hashes was already there (or occurs twice here).
     bool insert_all(std::vector<uint64_t> &hs, std::vector<uint64_t> &scratch)
     {
         if (hs.empty()) return false;
@@ -317,7 +447,20 @@ public:
         memcpy(at, count, sizeof at);
         for (uint64_t h : hs) scratch[at[h >> (64 - SHARD_BITS)]++] = h;
         bool dup = false;
-        for (size_t k = 0; k < N_SHARDS; ++k) {
+        // every caller starts its round over the shards somewhere else: workers that finish their chunks together would otherwise
+        // queue up behind each other's locks shard after shard
+        const size_t first = (size_t)rot_.fetch_add(0x9E37u, std::memory_order_relaxed) & (N_SHARDS - 1);
+        auto request = [&](size_t k) {                       // (the table may be replaced meanwhile: a prefetch is only a hint)
+            const Shard &sh = shards_[k];
+            const uint64_t *base = sh.pf_base.load(std::memory_order_relaxed);
+            const size_t mask = sh.pf_mask.load(std::memory_order_relaxed);
+            if (!base) return;
+            for (uint32_t i = count[k]; i < count[k + 1]; ++i) __builtin_prefetch(base + ((scratch[i] * 0xD6E8FEB86659FD93ull >> 20) & mask), 1);
+        };
+        for (size_t kk = 0; kk < LOOKAHEAD; ++kk) request((first + kk) & (N_SHARDS - 1));
+        for (size_t kk = 0; kk < N_SHARDS; ++kk) {
+            const size_t k = (first + kk) & (N_SHARDS - 1);
+            if (kk + LOOKAHEAD < N_SHARDS) request((first + kk + LOOKAHEAD) & (N_SHARDS - 1));
             if (count[k] == count[k + 1]) continue;
             Shard &sh = shards_[k];
             std::lock_guard<std::mutex> lk(sh.m);
@@ -329,11 +472,20 @@ public:
 private:
     static const int SHARD_BITS = 10;
     static const size_t N_SHARDS = 1u << SHARD_BITS;
+    static const size_t LOOKAHEAD = 24;
     static const uint64_t EMPTY_ALIAS = 0x9E3779B97F4A7C15ull;   // 0 marks an empty slot
-    struct Shard { std::mutex m; std::vector<uint64_t> slots; size_t n = 0; };
+    struct Shard {
+        std::mutex m; std::vector<uint64_t> slots; size_t n = 0;
+        std::atomic<const uint64_t *> pf_base{nullptr}; std::atomic<size_t> pf_mask{0};   // where to prefetch (written under the lock)
+    };
+    static void publish(Shard &sh)
+    {
+        sh.pf_base.store(sh.slots.data(), std::memory_order_relaxed);
+        sh.pf_mask.store(sh.slots.size() - 1, std::memory_order_relaxed);
+    }
     static bool insert_locked(Shard &sh, uint64_t h)
     {
-        if (sh.slots.empty()) { sh.slots.assign(1u << 10, 0); }
+        if (sh.slots.empty()) { sh.slots.assign(1u << 10, 0); publish(sh); }
         size_t mask = sh.slots.size() - 1, s = (h * 0xD6E8FEB86659FD93ull >> 20) & mask;
         while (sh.slots[s]) {
             if (sh.slots[s] == h) return true;
@@ -343,6 +495,7 @@ private:
         if (++sh.n * 10 > sh.slots.size() * 6) {
             std::vector<uint64_t> old;
             old.swap(sh.slots);
+            sh.pf_base.store(nullptr, std::memory_order_relaxed);
             sh.slots.assign(old.size() * 2, 0);
             mask = sh.slots.size() - 1;
             for (uint64_t v : old)
@@ -351,10 +504,12 @@ private:
                     while (sh.slots[t]) t = (t + 1) & mask;
                     sh.slots[t] = v;
                 }
+            publish(sh);
         }
         return false;
     }
     std::vector<Shard> shards_;
+    std::atomic<uint32_t> rot_{0};
 };
 
 // ---- the decoder --------------------------------------------------------------------------------
@@ -433,6 +588,7 @@ public:
     {
         st = DecodeStats();
         RunHeadSet heads;
+        if (assume_grouped && comp_ == Compression::none) heads.reserve(std::min<uint64_t>(file_.n / 64, 64ull << 20));   // a guess from the file size (16 bytes per expected read, at most 1 GB); more reads than that rehash
         std::atomic<bool> came_back(false);
         n_threads = std::max(1, n_threads);
         const int n_parse = std::max(1, comp_ == Compression::bgzf ? n_threads / 2 : n_threads - 1);
@@ -440,8 +596,8 @@ public:
         const uint32_t n_refs = (uint32_t)header_.names.size();
         OrderedStage<ParseJob, ParsedChunk> parse(n_parse, (size_t)n_parse * 3 + 2, [this, n_refs, assume_grouped, &heads, &came_back](ParseJob &job, ParsedChunk &out) {
             const size_t guess = (job.end - job.begin) / (is_bam_ ? 200 : 250) + 16;
-            out.hash.reserve(guess); out.key_off.reserve(guess); out.key_len.reserve(guess); out.ref.reserve(guess); out.pos.reserve(guess);
-            out.keys.reserve(guess * 24);
+            out.clear();                                      // (a recycled chunk keeps its arrays)
+            out.ensure(guess);
             if (!job.head.empty()) {
                 if (is_bam_) parse_bam_record(job.head.data(), job.head.size(), n_refs, out, nullptr);
                 else parse_sam_line(job.head.data(), job.head.data() + job.head.size(), names_, out, nullptr);
@@ -453,7 +609,8 @@ public:
             if (assume_grouped && out.error.empty()) {        // run heads inside the chunk; record 0 is the consumer's business
                 const size_t n = out.size();
                 out.new_run.assign(n, 0);
-                std::vector<uint64_t> hs, scratch;
+                std::vector<uint64_t> &hs = out.heads, &scratch = out.scratch;
+                hs.clear();
                 hs.reserve(n);
                 for (size_t i = 1; i < n; ++i)
                     if (!out.same_key(i, i - 1)) { out.new_run[i] = 1; hs.push_back(out.hash[i]); }
@@ -486,7 +643,9 @@ public:
         ParsedChunk ch;
         bool ok = true;
         uint64_t next_id = 0;                                 // grouped fast path: runs seen so far
-        while (parse.pop(ch)) {
+        for (;;) {
+            parse.recycle(std::move(ch));                     // the chunk consumed last: its arrays serve another job
+            if (!parse.pop(ch)) break;
             if (!ch.error.empty()) { err = ch.error; ok = false; break; }
             st.records_in_file += ch.n_records;
             const size_t n = ch.size();

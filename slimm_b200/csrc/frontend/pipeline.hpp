@@ -90,6 +90,13 @@ public:
         cv_done_.notify_all();
         cv_space_.notify_all();
     }
+    // hands a consumed result back: its buffers go to the next job instead of to the allocator (a result of this pipeline is
+    // megabytes of arrays; fresh ones cost a page fault per 4 KB, and the threads' faults serialise in the kernel)
+    void recycle(Out &&out)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (free_.size() < max_inflight_ + workers_.size()) free_.push_back(std::move(out));
+    }
     bool pop(Out &out)
     {
         std::unique_lock<std::mutex> lk(m_);
@@ -108,14 +115,15 @@ private:
     {
         for (;;) {
             std::pair<uint64_t, In> job;
+            Out out;
             {
                 std::unique_lock<std::mutex> lk(m_);
                 cv_work_.wait(lk, [&] { return !todo_.empty() || closed_; });
                 if (todo_.empty() || aborted_) return;
                 job = std::move(todo_.front());
                 todo_.pop_front();
+                if (!free_.empty()) { out = std::move(free_.back()); free_.pop_back(); }   // a recycled result: fn_ resets it
             }
-            Out out;
             fn_(job.second, out);
             {
                 std::lock_guard<std::mutex> lk(m_);
@@ -130,6 +138,7 @@ private:
     std::condition_variable cv_work_, cv_done_, cv_space_;
     std::deque<std::pair<uint64_t, In>> todo_;
     std::map<uint64_t, Out> done_;
+    std::vector<Out> free_;
     uint64_t pushed_ = 0, popped_ = 0;
     bool closed_ = false, aborted_ = false;
     std::vector<std::thread> workers_;

@@ -1222,9 +1222,33 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
             if (my_steps) {
                 // bins [wid * SPW * 64, (wid + 1) * SPW * 64) of the slice, eight steps at a time; lane l holds bins 2l, 2l+1 of a step
                 u32 nz = 0, sum = 0, unz = 0, usum = 0;
+                u32 nzp = 0, sump = 0;                         // PACKED: {cov | uniq_cov << 16} partial counts / sums of the fast path below
 #pragma unroll 1
                 for (int h = 0; h < SPW / 8; ++h) {
                     const u32 wb = (wid * SPW + h * 8) * 64 + 2 * lane;
+                    if (PACKED && cnt && (u32)(h * 8 + 8) <= my_steps && ((step0 + h * 8 + 8) << 6) <= g_end) {
+                        // eight whole steps inside the current reference (almost always): the statistics are taken from the packed
+                        // words as they are - a slice with fewer than 65536 items cannot carry from one half into the other, so ONE
+                        // add per word sums cov and uniq_cov together - and the words go out without being unpacked (the packed
+                        // pass was bound by instruction issue: 31 thread instructions per bin, ncu r2z)
+                        uint2 w[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) w[t] = *reinterpret_cast<const uint2 *>(sh + wb + t * 64);
+                        if (hist4) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                if (COMPACT) __stcs(reinterpret_cast<uint2 *>(hist4) + (step0 + h * 8 + t) * 32 + lane, w[t]);
+                                else __stcs(hist4 + (step0 + h * 8 + t) * 32 + lane, make_uint4(w[t].x & 0xFFFFu, w[t].x >> 16, w[t].y & 0xFFFFu, w[t].y >> 16));
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            sump += w[t].x + w[t].y;
+                            nzp += min(w[t].x & 0xFFFFu, 1u) + min(w[t].y & 0xFFFFu, 1u) + ((min(w[t].x >> 16, 1u) + min(w[t].y >> 16, 1u)) << 16);
+                        }
+                        continue;
+                    }
+                    if (PACKED) { nz += nzp & 0xFFFFu; unz += nzp >> 16; sum += sump & 0xFFFFu; usum += sump >> 16; nzp = sump = 0; }
                     uint4 v[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
@@ -1264,6 +1288,7 @@ k_fine_accumulate(const u32 *__restrict__ fine, const u32 *__restrict__ start, u
                     }
                 }
                 if (cnt) {
+                    if (PACKED) { nz += nzp & 0xFFFFu; unz += nzp >> 16; sum += sump & 0xFFFFu; usum += sump >> 16; }
                     nz = warp_sum(nz); sum = warp_sum(sum); unz = warp_sum(unz); usum = warp_sum(usum);
                     if (lane == 0 && (nz | unz)) {
                         atomicAdd(stats + 4 * g + 0, nz); atomicAdd(stats + 4 * g + 1, sum);

@@ -188,3 +188,23 @@ def test_fallback_to_the_name_table_stops_the_first_pass_at_once(tmp_path):
 
     exact, default = best(("--exact-ids",)), best(())
     assert default < 1.45 * exact + 0.25, (default, exact)
+
+
+def test_batched_parser_equals_line_parser(tmp_path):
+    """The pipeline's chunk parser (eight lines at a time, prefetched contig look-ups, SWAR number parsing) gives what the line
+    parser gives - records, counters and error text - on random pieces of a SAM file, most of them damaged at random
+    (tests/cpp/parser_equiv.cpp)."""
+    rng = np.random.default_rng(11)
+    tax, accs = synth.make_taxonomy(3000)
+    contigs = synth.make_contigs(3000, rng, accs, 200_000, 900_000)
+    rec = synth.make_records(contigs, 300_000, rng, multi_frac=0.3)
+    sam = tmp_path / "in.sam"
+    synth.write_sam_for_records(str(sam), contigs, rec)
+    exe = tmp_path / "parser_equiv"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "parser_equiv.cpp")
+    inc = os.path.join(root, "slimm_b200", "csrc", "frontend")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", inc, src, "-lz", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(sam)], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad 0 bad_numbers 0" in r.stdout, r.stdout + r.stderr
