@@ -563,6 +563,16 @@ def main():
         ev1.record(stream)
         torch.cuda.synchronize()
         e2e["h2d_probe_GBps_this_rank"] = 3 * 4 * probe.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        if world > 1:                                             # every rank's link while all of them copy: where the host side saturates
+            mine = torch.tensor([e2e["h2d_probe_GBps_this_rank"]], dtype=torch.float64, device=dev)
+            allp = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allp, mine)
+            e2e["h2d_probe_GBps_per_rank"] = [round(float(a[0]), 1) for a in allp]
+            e2e["h2d_probe_GBps_sum"] = round(sum(float(a[0]) for a in allp), 1)
+            try:
+                e2e["cpu_affinity_this_rank"] = len(os.sched_getaffinity(0))
+            except Exception:
+                pass
         del probe
         if packed:
             del h_pos, h_ref, h_bits

@@ -128,6 +128,7 @@ struct ParsedChunk {
     std::vector<int32_t> pos;
     std::vector<char> keys;          // read keys back to back (keys_used bytes)
     std::vector<uint8_t> new_run;    // grouped-input fast path: record i >= 1 starts another read than record i - 1
+    std::vector<uint32_t> local_id;  // grouped-input fast path: runs started between record 0 and record i (inclusive)
     std::vector<uint64_t> heads, scratch;   // grouped-input fast path: the chunk's run-head hashes (kept here so that a recycled chunk brings its buffers)
     size_t n = 0, keys_used = 0;
     uint64_t n_records = 0;          // records seen, kept or not
@@ -612,8 +613,13 @@ public:
                 std::vector<uint64_t> &hs = out.heads, &scratch = out.scratch;
                 hs.clear();
                 hs.reserve(n);
-                for (size_t i = 1; i < n; ++i)
-                    if (!out.same_key(i, i - 1)) { out.new_run[i] = 1; hs.push_back(out.hash[i]); }
+                out.local_id.resize(n);
+                uint32_t runs = 0;                              // runs that START inside the chunk behind record 0
+                if (n) out.local_id[0] = 0;
+                for (size_t i = 1; i < n; ++i) {
+                    if (!out.same_key(i, i - 1)) { out.new_run[i] = 1; hs.push_back(out.hash[i]); ++runs; }
+                    out.local_id[i] = runs;                     // the record's read id relative to record 0's: the consumer only adds a base
+                }
                 if (heads.insert_all(hs, scratch)) came_back.store(true, std::memory_order_relaxed);
             }
         });
@@ -651,21 +657,28 @@ public:
             const size_t n = ch.size();
             if (assume_grouped) {
                 if (came_back.load(std::memory_order_relaxed)) { st.not_grouped = true; ok = false; break; }
-                for (size_t i = 0; i < n; ++i) {
-                    bool fresh;
-                    if (i) fresh = ch.new_run[i] != 0;
-                    else {                                     // does the chunk continue the previous chunk's last read?
-                        const char *key = ch.keys.data() + ch.key_off[0];
-                        fresh = !(have_prev && ch.hash[0] == prev_hash && prev_key.size() == ch.key_len[0] && memcmp(prev_key.data(), key, ch.key_len[0]) == 0);
-                        if (fresh && heads.insert(ch.hash[0])) came_back.store(true, std::memory_order_relaxed);
+                if (n) {
+                    // does the chunk continue the previous chunk's last read?  Everything else was settled by the worker: record i
+                    // has the id of record 0 plus local_id[i], so the serial part of the decoder is one add and two copies per record
+                    const char *key = ch.keys.data() + ch.key_off[0];
+                    const bool fresh = !(have_prev && ch.hash[0] == prev_hash && prev_key.size() == ch.key_len[0] && memcmp(prev_key.data(), key, ch.key_len[0]) == 0);
+                    if (fresh && heads.insert(ch.hash[0])) came_back.store(true, std::memory_order_relaxed);
+                    if (fresh) ++next_id;
+                    const uint64_t id0 = next_id - 1;
+                    next_id = id0 + ch.local_id[n - 1] + 1;
+                    if (next_id > 0xFFFFFFFEull) { err = "more than 2^32-2 distinct reads"; ok = false; break; }
+                    for (size_t i = 0; i < n;) {
+                        if (batch.n == batch.cap) batch = sink(batch);   // the sink hands back the batch to fill next (n = records it already holds)
+                        const size_t m = std::min(n - i, batch.cap - batch.n);
+                        uint32_t *rid = batch.read_id + batch.n;
+                        const uint32_t *loc = ch.local_id.data() + i;
+                        const uint32_t base = (uint32_t)id0;
+                        for (size_t k = 0; k < m; ++k) rid[k] = base + loc[k];
+                        memcpy(batch.ref_id + batch.n, ch.ref.data() + i, m * 4);
+                        memcpy(batch.begin_pos + batch.n, ch.pos.data() + i, m * 4);
+                        batch.n += m;
+                        i += m;
                     }
-                    if (fresh) {
-                        if (next_id >= 0xFFFFFFFEull) { err = "more than 2^32-2 distinct reads"; ok = false; break; }
-                        ++next_id;
-                    }
-                    if (batch.n == batch.cap) batch = sink(batch);   // the sink hands back the batch to fill next (n = records it already holds)
-                    batch.read_id[batch.n] = (uint32_t)(next_id - 1); batch.ref_id[batch.n] = ch.ref[i]; batch.begin_pos[batch.n] = ch.pos[i];
-                    ++batch.n;
                 }
                 if (!ok) break;
                 if (n) {

@@ -504,7 +504,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     }
     k_fine_scan<<<FINE_SCAN_CL, 1024, 0, ctx->stream>>>(ctx->d_fine_cnt, (u32)n_fine, ctx->d_fine_start, ctx->d_fine_cursor, ctx->d_fine_hot, n_hot, vhot, n_vhot);
     if (n_tiles) {
-        static const int fnt = getenv("SLIMM_FINE_SPLIT_NT") ? atoi(getenv("SLIMM_FINE_SPLIT_NT")) : 256;   // tile shape (experiments)
+        const int fnt = getenv("SLIMM_FINE_SPLIT_NT") ? atoi(getenv("SLIMM_FINE_SPLIT_NT")) : 256;   // tile shape (experiments)
         if (fnt >= 512) {
             const u64 tiles = (n_cap + 512 * FINE_ITEMS - 1) / (512 * FINE_ITEMS);
             const int sgrid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ctx->sm_count * 2));
@@ -570,12 +570,12 @@ static bool split_needs_exact(u32 shift, u32 n_buckets) { return std::min<u32>(0
 template <bool PEER>
 static void launch_k_split(slimm_gpu_ctx *ctx, int sgrid, const u32 *items, u32 n, u32 shift, u32 n_buckets, u32 *out, u32 *const *dest)
 {
-    static const int nt = getenv("SLIMM_SPLIT_NT") ? atoi(getenv("SLIMM_SPLIT_NT")) : 512;
+    const int nt = getenv("SLIMM_SPLIT_NT") ? atoi(getenv("SLIMM_SPLIT_NT")) : 512;
     const int per_sm = nt >= 1024 ? 1 : 2;
     const u64 n_tiles = ((u64)n + SPLIT_TILE - 1) / SPLIT_TILE;
     const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * per_sm));
     (void)sgrid;
-    static const int bulk = getenv("SLIMM_SPLIT_BULK") ? atoi(getenv("SLIMM_SPLIT_BULK")) : 0;   // tiles through the bulk-copy engine (local splits)
+    const int bulk = getenv("SLIMM_SPLIT_BULK") ? atoi(getenv("SLIMM_SPLIT_BULK")) : 0;   // tiles through the bulk-copy engine (local splits)
     if (!PEER && bulk && ((uintptr_t)items & 15) == 0 && n_buckets <= SPLITB_NT) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_split_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLITB_SMEM); attr = true; }
@@ -1030,6 +1030,7 @@ int slimm_gpu_split_to_peers(slimm_gpu_ctx *ctx, const uint32_t *all_counts, uin
         if (q == me) mine = off;
     }
     ctx->n_recv = mine;
+    ctx->n_recv_on_device = false; ctx->routed = false;         // (a context may have used the device-planned exchange for its last sample)
     if (n_recv) *n_recv = mine;
     if (ctx->split_pending) {
         TimeScope ts(ctx, SLIMM_GPU_T_SPLIT);
