@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslimm_gpu.so")
+LIB_PATH = os.environ.get("SLIMM_GPU_LIB") or os.path.join(_HERE, "libslimm_gpu.so")   # SLIMM_GPU_LIB: another build of the same library (A/B runs)
 
 KEEP_UNIQ_COV2 = 1
 READ_RESULTS = 2

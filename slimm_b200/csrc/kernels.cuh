@@ -965,7 +965,9 @@ k_fine_count(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr /* num
 // stores of one SM alone would take longer than everything else: eight SMs share them).
 // Also lists the HOT slices (65536 items or more: the ones the packed accumulate leaves to the wide one) in hot[0 .. *n_hot) and the
 // VERY hot ones (FINE_VHOT items or more: a cluster of CTAs shares each of them) in vhot[0 .. *n_vhot) instead.
+#ifndef FINE_VHOT
 #define FINE_VHOT (1u << 19)
+#endif
 #define FINE_SCAN_CL 8
 __global__ void __cluster_dims__(FINE_SCAN_CL, 1, 1) __launch_bounds__(1024)
 k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u32 *__restrict__ cursor, u32 *__restrict__ hot, u32 *__restrict__ n_hot,
