@@ -478,6 +478,7 @@ int slimm_gpu_sync_uploads(slimm_gpu_ctx *ctx)
 // Accumulate + per-reference statistics in shared memory, fine slice by fine slice.  items: grouped by coarse slice
 // (their number is sd->total_items on the device, or n_given); n_cap bounds it on the host; out_buf receives the items
 // grouped by fine slice; [lo_bin, hi_bin) are the bins this rank owns.
+static bool force_exact();
 static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_ptr, u64 n_given, u64 n_cap, u32 *out_buf, u64 lo_bin, u64 hi_bin)
 {
     const u64 n_fine = (ctx->Bp + FINE_BINS - 1) >> FINE_SHIFT;
@@ -491,7 +492,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
     if (!ctx->d_fine_hot) CU(cudaMalloc(&ctx->d_fine_hot, 2 * 65536 * 4));   // slices with >= 65536 items: fewer than 2^16 of them; second half: the very hot ones
     TimeScope ts(ctx, SLIMM_GPU_T_ACCUM);
     CU(cudaMemsetAsync(ctx->d_fine_cnt, 0, (n_fine + 8) * 4, ctx->stream));
-    const bool exact = n_fine > FINE_WRAP_SAFE;               // (bins within 2^23 of 2^31: the kernels take the plain 32-bit slice difference)
+    const bool exact = n_fine > FINE_WRAP_SAFE || force_exact();               // (bins within 2^23 of 2^31: the kernels take the plain 32-bit slice difference)
     // spare words behind the counts (zeroed with them): ticket of the packed pass, number of hot slices, ticket of the hot pass, number of very hot slices
     u32 *ticket = ctx->d_fine_cnt + n_fine, *n_hot = ticket + 1, *hot_ticket = ticket + 2, *n_vhot = ticket + 3;
     u32 *vhot = ctx->fine_cluster && ctx->fine_packed ? ctx->d_fine_hot + 65536 : nullptr;
@@ -564,7 +565,9 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
 }
 
 // ITEM_SKIP is ranked in the slot min(0x7FFFFFFF >> shift, MAX_BUCKETS); when the slices in use reach that slot the kernels test for it explicitly
-static bool split_needs_exact(u32 shift, u32 n_buckets) { return std::min<u32>(0x7FFFFFFFu >> shift, MAX_BUCKETS) < n_buckets; }
+// (SLIMM_FORCE_EXACT=1 takes the EXACT instantiations regardless: they are otherwise only reached with more than 2.13e9 bins)
+static bool force_exact() { const char *e = getenv("SLIMM_FORCE_EXACT"); return e && atoi(e) != 0; }
+static bool split_needs_exact(u32 shift, u32 n_buckets) { return force_exact() || std::min<u32>(0x7FFFFFFFu >> shift, MAX_BUCKETS) < n_buckets; }
 
 // K1b: shape of the split CTAs (SLIMM_SPLIT_NT = 256 | 512 | 1024 threads over the same 8192-item tile)
 template <bool PEER>

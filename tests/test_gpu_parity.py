@@ -219,12 +219,12 @@ def test_alternative_paths_agree(env, value, monkeypatch):
 
 @pytest.mark.parametrize("env,value", [("SLIMM_GPU_ACC", "l2"), ("SLIMM_GPU_COV", "window"), ("SLIMM_GPU_FINE", "wide"),
                                        ("SLIMM_GPU_COMPACT_BINS", "0"), ("SLIMM_GPU_FINE_CLUSTER", "0"), ("SLIMM_SPLIT_BULK", "1"),
-                                       ("SLIMM_FINE_SPLIT_NT", "512")])
+                                       ("SLIMM_FINE_SPLIT_NT", "512"), ("SLIMM_FORCE_EXACT", "1")])
 def test_alternative_kernels_agree(env, value, monkeypatch):
     """The other kernels stay selectable for A/B runs (64-bit REDs into L2-resident slices instead of the shared-memory
     fine slices; sliding-window coverage instead of warp-private tiles; wide counters only; interleaved instead of compact
-    bins; hot slices without clusters; bulk-copy tile staging in the coarse split; 512-thread fine split): same results, bins
-    included."""
+    bins; hot slices without clusters; bulk-copy tile staging in the coarse split; 512-thread fine split; the EXACT instantiations of
+    the split / count kernels that histograms within 2^23 bins of 2^31 take): same results, bins included."""
     contigs, rec, lineage = _synthetic(300, 1_500_000, 5, len_lo=300_000, len_hi=900_000, multi_frac=0.4)
     w = 10
     res = oracle.run(contigs.lengths, lineage, w, 100, 0.9, rec.read_id, rec.ref_id, rec.begin_pos)
