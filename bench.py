@@ -333,7 +333,8 @@ def main():
                        "bins": ("written back to HBM (fetchable)" if args.bins == "keep" else
                                 "consumed in shared memory, not written back (profile-only run, SLIMM_GPU_SKIP_BINS)"),
                        "exchange": "none (one GPU)" if world == 1 else
-                                   "peer-to-peer stores fused into the split kernel (NCCL all-to-all of the items when peer mapping is unavailable)"}}
+                                   "items grouped by histogram slice locally, every owner's contiguous block copied into its buffer over NVLink peer memory "
+                                   "(k_peer_copy; NCCL all-to-all of the items when peer mapping is unavailable)"}}
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
