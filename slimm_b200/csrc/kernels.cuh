@@ -831,14 +831,16 @@ k_peer_copy_plan(const u32 *__restrict__ all_counts /*[n_ranks][n_slices]*/, u32
         plan->src_off[tid] = off;
         plan->len[tid] = s_from[tid][me];
         if ((u64)all > recv_cap) atomicOr(overflow, 1u);
-        if (tid == me) *n_recv = all;
+        if (tid == me) *n_recv = (u64)all > recv_cap ? 0u : all;    // (on overflow nothing is copied and nothing is read)
     }
 }
 
 #define PCOPY_CHUNK 8192u
 __global__ void __launch_bounds__(256)
-k_peer_copy(const u32 *__restrict__ grouped, const CopyPlan *__restrict__ plan, u32 n_ranks, u32 me)
+k_peer_copy(const u32 *__restrict__ grouped, const CopyPlan *__restrict__ plan, u32 n_ranks, u32 me, const u32 *__restrict__ overflow)
 {
+    if (*overflow) return;                                         // some receive buffer is too small (every rank sees that from the table): nobody
+                                                                   // writes, slimm_gpu_get_summary reports SLIMM_GPU_ERANGE on every rank
     const u32 tid = threadIdx.x;
     for (u32 k = 0; k < n_ranks; ++k) {
         const u32 q = (me + 1 + k + blockIdx.x) % n_ranks;         // CTAs start on different links

@@ -1072,7 +1072,7 @@ int slimm_gpu_split_to_peers_device(slimm_gpu_ctx *ctx, const uint32_t *d_all_co
             launch_k_split<false>(ctx, 0, ctx->d_items, n, ctx->bucket_shift, ns, ctx->d_grouped, nullptr);
             const u64 chunks = ((u64)n + PCOPY_CHUNK - 1) / PCOPY_CHUNK + ctx->shard_n;
             const int grid = (int)std::max<u64>(1, std::min<u64>(chunks, (u64)ctx->sm_count * 4));
-            k_peer_copy<<<grid, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_copy_plan, ctx->shard_n, ctx->shard_rank);
+            k_peer_copy<<<grid, 256, 0, ctx->stream>>>(ctx->d_grouped, ctx->d_copy_plan, ctx->shard_n, ctx->shard_rank, ctx->d_n_recv + 1);
             ctx->launches += 2;
             ctx->split_pending = false;
         }
