@@ -31,6 +31,8 @@ _PEER_MODES = {"p2p_split": "0", "p2p_route": "1", "p2p_blocks": "2"}   # SLIMM_
 
 
 def _worker(rank, world, port, w, exchange, out):
+    small_buffer = exchange.endswith("+small_buffer")
+    exchange = exchange.split("+")[0]
     p2p = exchange in _PEER_MODES
     if p2p:
         os.environ["SLIMM_PEER_ROUTE"] = _PEER_MODES[exchange]
@@ -54,11 +56,15 @@ def _worker(rank, world, port, w, exchange, out):
                 gpu.reset()
                 gpu.set_shard(rank, world)
                 if p2p and it == 0:                  # items travel as peer-to-peer stores inside the split instead of NCCL
-                    if not sdist.connect_peers(gpu, dev, int(rec.read_id.size)):
+                    if not sdist.connect_peers(gpu, dev, 1000 if small_buffer else int(rec.read_id.size)):
                         out.put((rank, "skip: CUDA IPC peer mapping is not available on this box"))
                         return
                 gpu.push(rec.read_id[a:b], rec.ref_id[a:b], rec.begin_pos[a:b])
                 sdist.run_sharded(gpu, dev, 0.9, 0, int(rec.read_id.size))
+                if small_buffer:                     # every rank sees from the all-gathered table that a receive buffer is too small:
+                    with pytest.raises(api.SlimmGpuError):   # nothing is copied, the run completes, the result is refused
+                        gpu.summary()
+                    continue
                 s = gpu.summary()
                 assert (s.hits_count, s.matches_count, s.uniq_matches_count, s.uniq_matches_count2) == \
                        (res.hits, res.n_reads, res.n_uniq, res.n_uniq2)
@@ -102,7 +108,7 @@ def _worker(rank, world, port, w, exchange, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["nccl_all_to_all", "p2p_split", "p2p_route", "p2p_blocks"])
+@pytest.mark.parametrize("exchange", ["nccl_all_to_all", "p2p_split", "p2p_route", "p2p_blocks", "p2p_blocks+small_buffer"])
 @pytest.mark.parametrize("w", [10, 1000])
 def test_two_gpus_match_oracle(w, exchange):
     """The four item exchanges: one NCCL all-to-all of the slice-grouped items; peer stores inside the split (runs per slice);
