@@ -1054,7 +1054,10 @@ k_fine_scan(const u32 *__restrict__ cnt, u32 n_fine, u32 *__restrict__ start, u3
 // scatter into the staging tile, bucket look-ups: l1tex 73-77 %), and the bursts of sixteen atomics per thread fill the MIO queue.)
 // NT threads x ITEMS items per tile (256 x 16, or 512 x 16: longer runs per fine slice and half as many tiles)
 template <int NT, int ITEMS>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 4)
+#ifndef FINE_SPLIT_OCC
+#define FINE_SPLIT_OCC 4          // CTAs of 256 threads per SM the register allocation of k_fine_split is bounded for
+#endif
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : FINE_SPLIT_OCC)
 k_fine_split(const u32 *__restrict__ items, const u32 *__restrict__ n_ptr, u32 n_given, u32 cshift, u32 *__restrict__ cursor,
              u32 *__restrict__ out)
 {

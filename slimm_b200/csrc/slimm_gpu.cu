@@ -511,7 +511,7 @@ static int fine_accumulate(slimm_gpu_ctx *ctx, const u32 *items, const u32 *n_pt
             const int sgrid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ctx->sm_count * 2));
             k_fine_split<512, FINE_ITEMS><<<sgrid, 512, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
         } else {
-            const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * 4));
+            const int sgrid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)ctx->sm_count * FINE_SPLIT_OCC));
             k_fine_split<256, FINE_ITEMS><<<sgrid, 256, 0, ctx->stream>>>(items, n_ptr, (u32)n_given, ctx->bucket_shift, ctx->d_fine_cursor, out_buf);
         }
     }
