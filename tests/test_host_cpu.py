@@ -67,3 +67,29 @@ def test_tree_consistency_classification():
     assert not api.db_is_tree_consistent(bad, taxa)           # taxon 2 on two levels
     taxa3 = dict(taxa); taxa3[5] = (6, "wrong rank")
     assert not api.db_is_tree_consistent(lin, taxa3)
+
+
+def test_traffic_json_matches_the_committed_capture(tmp_path):
+    """profiles/traffic.json (what bench.py reports as roofline.traffic) is what scripts/make_traffic_json.py makes of the committed
+    ncu CSV: every launch of the last complete step, per kernel group; the coverage kernel moves ~18.8 bytes per record at cfg5."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    prof = os.path.join(ROOT, "profiles")
+    committed = json.load(open(os.path.join(prof, "traffic.json")))
+    tag = committed["capture"]
+    csv5 = os.path.join(prof, f"{tag}_traffic_cfg5.csv")
+    assert os.path.exists(csv5), "the capture traffic.json names is not committed"
+    # run the script on a copy of the tree's profiles/ so that the tracked file stays untouched
+    work = tmp_path / "repo"
+    (work / "scripts").mkdir(parents=True)
+    (work / "profiles").mkdir()
+    shutil.copy(os.path.join(ROOT, "scripts", "make_traffic_json.py"), work / "scripts" / "make_traffic_json.py")
+    r = subprocess.run([sys.executable, str(work / "scripts" / "make_traffic_json.py"), tag, f"cfg5={csv5}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    made = json.load(open(work / "profiles" / "traffic.json"))
+    for group in ("coverage", "split", "accumulate", "assign"):
+        assert made["cfg5"][group]["dram_bytes_per_launch"] == committed["cfg5"][group]["dram_bytes_per_launch"]
+    assert 16.0 < made["cfg5"]["coverage"]["dram_bytes_per_record"] < 21.0
+    assert "k_fine_accumulate_cluster" in made["cfg5"]["accumulate"]["kernel"]
